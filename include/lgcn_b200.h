@@ -1,0 +1,234 @@
+/* lgcn_b200.h -- C ABI of the B200-native (sm_100a) LightGCN hot path.
+ *
+ * Drop-in boundary for the operators below the reference's Python module API
+ * (paths relative to the reference checkout /root/reference):
+ *
+ *   lgcn_graph_build      replaces gcn_norm's per-layer degree scatter + the implicit COO order
+ *                         that LGConv consumes           models/light_gcn.py:33  (PyG gcn_conv.py::gcn_norm)
+ *   lgcn_propagate_fwd    replaces `for conv in self.convs` + stack/mean/split
+ *                                                        models/light_gcn.py:29-38
+ *   lgcn_propagate_bwd    replaces autograd of the above (loss.backward())
+ *                                                        utils/train_test.py:94
+ *   lgcn_bpr_fwd_bwd      replaces the six row gathers + bpr_loss + their autograd
+ *                                                        utils/train_test.py:128-132, :18-64
+ *   lgcn_clip_adam        replaces clip_grad_norm_(1) + Adam.step (dense, both tables)
+ *                                                        utils/train_test.py:95-96, :236
+ *   lgcn_train_step       one call = the loop body       utils/train_test.py:88-96
+ *   lgcn_cluster_extract  replaces ClusterData partition/permute/__getitem__ + n_id remap
+ *                                                        data/dataset_handler.py:273-282
+ *   lgcn_partition_metis  the METIS call ClusterData makes (host, third-party library)
+ *                                                        data/dataset_handler.py:273
+ *   lgcn_score_topk       replaces normalise + matmul + sort + exclusion loop, batched over users
+ *                                                        utils/recommend.py:39-61, utils/train_test.py:191-197
+ *
+ * Conventions
+ *   - plain C types only: device pointers, sizes, a CUDA stream passed as void* (cudaStream_t).
+ *   - the CALLER allocates every output and workspace (sizes from the *_bytes queries);
+ *     the library keeps no global state and never allocates device memory.
+ *   - node ids are int64 at the boundary exactly as the reference passes them
+ *     (edge_index LongTensor [2,E], users 0..U-1, movies U..U+I-1), int32 internally.
+ *   - every function returns 0 on success or a negative LGCN_E_* code; lgcn_last_error()
+ *     gives the message for the calling thread.  No function synchronises the stream unless
+ *     its comment says so.
+ *   - embedding dimension is fixed at LGCN_DIM = 64 fp32 (256-byte rows), the reference's dim_h
+ *     (utils/train_test.py:274, models/light_gcn.py:14).
+ */
+#ifndef LGCN_B200_H
+#define LGCN_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGCN_DIM 64
+#define LGCN_ROW_SPLIT 512          /* max edges handled by one warp task                */
+
+#define LGCN_OK 0
+#define LGCN_E_INVALID   (-1)       /* bad argument (null pointer, negative size, K<1 ...) */
+#define LGCN_E_CUDA      (-2)       /* a CUDA runtime call or launch failed                */
+#define LGCN_E_WORKSPACE (-3)       /* workspace smaller than the *_bytes query            */
+#define LGCN_E_RANGE     (-4)       /* ids do not fit the int32 internal range             */
+#define LGCN_E_METIS     (-5)       /* METIS returned an error                             */
+
+const char *lgcn_last_error(void);
+int lgcn_version(void);
+
+/* One warp task: edges [begin,end) of `row` in one of the two CSRs.  slot < 0: the task owns
+ * the whole row.  slot >= 0: the row is split; this task writes partial `slot`, the row's
+ * first partial is `slot - part`, and it has `nparts` of them. */
+typedef struct lgcn_task {
+    int32_t row, begin, end, slot, part, nparts, pad0, pad1;
+} lgcn_task;
+
+/* Device-resident, immutable description of one edge list (built once per edge list and
+ * cached by the host side; the reference rebuilds the normalisation in every layer). */
+typedef struct lgcn_graph {
+    int32_t num_nodes, num_users;
+    int64_t num_edges;
+    int64_t num_triplets;            /* P = #edges with source < num_users (utils/helpers.py:98) */
+    /* CSR by TARGET (forward):   in_nbr = source ids, stable in original edge order */
+    const int32_t *in_ptr, *in_nbr, *in_trip;
+    /* CSR by SOURCE (backward):  out_nbr = target ids                               */
+    const int32_t *out_ptr, *out_nbr, *out_trip;
+    const float *dis;                /* [N] in-degree^-1/2, 0 where the in-degree is 0       */
+    const uint8_t *active;           /* [N] 1 if the node has any incident edge              */
+    const lgcn_task *in_tasks, *out_tasks;
+    int32_t n_in_tasks, n_out_tasks;       /* tasks are sorted by row                        */
+    int32_t n_in_user_tasks, n_out_user_tasks; /* how many of them have row < num_users      */
+    int32_t n_in_slots, n_out_slots;       /* partial slots (rows longer than LGCN_ROW_SPLIT) */
+    float *partials;                 /* [max(n_in_slots,n_out_slots) * 80] scratch            */
+    int32_t *slot_counters;          /* [max slots] zero between launches                     */
+    int32_t num_active;              /* nodes with active[n] == 1                             */
+    int32_t pad;
+} lgcn_graph;
+
+/* ---- K0: graph build ------------------------------------------------------------------ */
+
+/* Sizes (bytes) of the arrays a graph of N nodes / E edges needs; the caller allocates them. */
+typedef struct lgcn_graph_sizes {
+    size_t ptr_bytes;      /* in_ptr / out_ptr: (N+1) int32 each                   */
+    size_t nbr_bytes;      /* in_nbr / in_trip / out_nbr / out_trip: E int32 each  */
+    size_t dis_bytes;      /* N float                                              */
+    size_t active_bytes;   /* N uint8                                              */
+    size_t task_bytes;     /* upper bound for each task list                       */
+    size_t partial_bytes;  /* upper bound for partials                             */
+    size_t counter_bytes;  /* upper bound for slot_counters                        */
+    size_t workspace_bytes;/* temporary storage for lgcn_graph_build               */
+} lgcn_graph_sizes;
+
+int lgcn_graph_sizes_query(int64_t num_nodes, int64_t num_edges, lgcn_graph_sizes *out);
+
+/* Builds both CSRs, degrees, dis, active flags and task lists from edge_index [2,E] int64
+ * (row-major: E sources then E targets, device memory).  `g` is a HOST struct whose pointer
+ * fields the caller has pointed at device arrays of the queried sizes; the scalar fields are
+ * filled on return.  SYNCHRONISES the stream once (to read the counts back).
+ * Returns LGCN_E_RANGE if N or E exceed int32, LGCN_E_INVALID if an id is outside [0,N) or an
+ * edge is not user<->movie (source<U xor target<U): the reference's two triplet masks
+ * (utils/helpers.py:98-99) only agree on bipartite lists. */
+int lgcn_graph_build(const int64_t *edge_index, int64_t num_edges, int64_t num_nodes,
+                     int64_t num_users, lgcn_graph *g, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
+/* ---- K1/K2: propagation ----------------------------------------------------------------- */
+
+/* final[N,64] = (sum_{k=0..K} A^k e0) / (K+1)^2 with A[c,r] = dis[r] dis[c] per edge r->c
+ * (models/light_gcn.py:28-40).  e0 is given as the two weight tables.  work: (K-1)*N*64 floats
+ * (none for K == 1).  rnorm (optional, [N]) receives 1/||final[n]||_2. */
+int lgcn_propagate_fwd(const lgcn_graph *g, const float *user_w, const float *item_w,
+                       int num_layers, float *final_out, float *rnorm, float *work,
+                       size_t work_bytes, void *stream);
+
+/* grad_e0[N,64] = (sum_{k=0..K} (A^T)^k G) / (K+1)^2, evaluated Horner-style.  work:
+ * 2*N*64 floats (none for K == 0).  If reg_coef != 0 the BPR regulariser's gradient
+ * reg_coef * cnt[n] * e0[n] is added and sum(cnt * ||e0||^2) goes to accum[1]; the squared
+ * norm of grad_e0 is ADDED to accum[2] (double, device).  cnt may be null when reg_coef == 0. */
+int lgcn_propagate_bwd(const lgcn_graph *g, const float *grad_final, int num_layers,
+                       const float *user_w, const float *item_w, const int32_t *neg_count,
+                       float reg_coef, float *grad_e0, double *accum, float *work,
+                       size_t work_bytes, void *stream);
+
+/* One LGConv layer on its own: out[N,64] = A x (transpose = 0) or A^T x (transpose != 0) -- the
+ * reference's inner operator `conv(x=emb, edge_index=edge_index)` (models/light_gcn.py:33). */
+int lgcn_spmm(const lgcn_graph *g, const float *x, float *out, int transpose, void *stream);
+
+/* ---- K3: BPR loss forward + gradient w.r.t. the final embeddings ------------------------ */
+
+/* Triplets are (source u, target p, neg[t]) for the t-th edge with source < U in edge order
+ * (utils/helpers.py:84-102); neg [P] int64 item ids in [0,I).  Writes grad_final [N,64]
+ * (every row), neg_count [I] (histogram of neg), trip_scratch [2*P] floats, and ADDS
+ * sum_t softplus(10 (cos+ - cos-)) to accum[0] (double).  final/rnorm come from
+ * lgcn_propagate_fwd. */
+int lgcn_bpr_fwd_bwd(const lgcn_graph *g, const float *final_emb, const float *rnorm,
+                     const int64_t *neg, float *grad_final, int32_t *neg_count,
+                     float *trip_scratch, double *accum, void *stream);
+
+/* bpr_loss on six already-gathered [P,64] tensors (utils/train_test.py:18-51), for callers that
+ * compose compute_embeddings + bpr_loss themselves.  accum: 2 doubles of scratch; loss_out: device
+ * float (optional); gradients (optional, all six or none) are multiplied by *grad_scale (device
+ * float, null = 1). */
+int lgcn_bpr_rows(const float *uf, const float *u0, const float *pf, const float *p0, const float *nf,
+                  const float *n0, int64_t P, float coeff, double *accum, float *loss_out,
+                  const float *grad_scale, float *g_uf, float *g_u0, float *g_pf, float *g_p0,
+                  float *g_nf, float *g_n0, void *stream);
+
+/* ---- K6: clip_grad_norm_(max_norm) + Adam ------------------------------------------------ */
+
+typedef struct lgcn_adam {
+    float lr, beta1, beta2, eps, max_norm;
+    int32_t pad;
+    int64_t *step;          /* device int64: incremented by lgcn_step_begin             */
+    float *m, *v;           /* [N,64] exp_avg / exp_avg_sq                              */
+} lgcn_adam;
+
+/* Zeroes accum[0..3] and increments *opt->step (one tiny launch). */
+int lgcn_step_begin(const lgcn_adam *opt, double *accum, void *stream);
+
+/* grad scaled by min(1, max_norm / (sqrt(accum[2]) + 1e-6)), then torch.optim.Adam's update
+ * on both tables.  Also writes loss = -accum[0]/(10 P) + bpr_coeff/(64 P) * accum[1] to
+ * loss_out[0] if loss_out != null. */
+int lgcn_clip_adam(const lgcn_adam *opt, float *user_w, float *item_w, int64_t num_users,
+                   int64_t num_items, const float *grad, const double *accum,
+                   int64_t num_triplets, float bpr_coeff, float *loss_out, void *stream);
+
+/* ---- fused training step ------------------------------------------------------------------ */
+
+typedef struct lgcn_step_buffers {
+    float *final_emb;      /* [N,64] */
+    float *rnorm;          /* [N]    */
+    float *grad_final;     /* [N,64] */
+    float *grad_e0;        /* [N,64] */
+    float *work;           /* max(K-1, 2) * N * 64 floats */
+    size_t work_bytes;
+    int32_t *neg_count;    /* [I]    */
+    float *trip_scratch;   /* [2*Pmax] */
+    double *accum;         /* [4]    */
+} lgcn_step_buffers;
+
+/* utils/train_test.py:88-96 for one batch: forward, BPR loss, backward, clip, Adam.
+ * loss_out: device float receiving this batch's loss (the reference's train_loss.item(),
+ * read back by the caller whenever it chooses -- no per-step sync). */
+int lgcn_train_step(const lgcn_graph *g, float *user_w, float *item_w, int num_layers,
+                    const int64_t *neg, float bpr_coeff, const lgcn_adam *opt,
+                    const lgcn_step_buffers *buf, float *loss_out, void *stream);
+
+/* Loss only (evaluate(), utils/train_test.py:153-156): forward + BPR value, no gradients. */
+int lgcn_eval_loss(const lgcn_graph *g, const float *user_w, const float *item_w, int num_layers,
+                   const int64_t *neg, float bpr_coeff, const lgcn_step_buffers *buf,
+                   float *loss_out, void *stream);
+
+/* ---- K4: Cluster-GCN sub-graph extraction ------------------------------------------------- */
+
+/* Host call into METIS with torch_sparse's arguments (no weights, default options, kway).
+ * indptr [N+1], index [E] and part_out [N] are HOST int64 arrays. */
+int lgcn_partition_metis(int64_t num_nodes, const int64_t *indptr, const int64_t *index,
+                         int64_t num_parts, int64_t *part_out);
+
+size_t lgcn_cluster_extract_workspace_bytes(int64_t num_nodes, int64_t num_edges, int64_t num_parts);
+
+/* Given train edges [2,E] int64 and the partition vector cluster [N] int64 (device), writes the
+ * concatenation over parts p = 0..P-1 of {(r,c): cluster[r]==cluster[c]==p} ordered by
+ * (inv[r], inv[c]) -- inv = inverse of the stable sort of `cluster` -- as GLOBAL ids into
+ * out_edges [2,E] (row-major with stride E), and part_ptr [P+1] offsets into it (int64).
+ * part_ptr[P] = number of intra-cluster edges kept. */
+int lgcn_cluster_extract(const int64_t *edge_index, int64_t num_edges, int64_t num_nodes,
+                         const int64_t *cluster, int64_t num_parts, int64_t *out_edges,
+                         int64_t *part_ptr, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- K5: scoring GEMM + train-edge mask + top-k ------------------------------------------- */
+
+/* For users [u_begin,u_end): score(u,i) = <U[u],I[i]> (rows optionally L2-normalised first, as
+ * utils/recommend.py:39-40), items listed in the user's exclusion CSR row (excl_ptr [U+1],
+ * excl_idx sorted item ids; may be null) are removed, top-k by (score desc, id asc) written to
+ * topk_idx [n_users,k] int32 and topk_val [n_users,k].  The score matrix is never stored. */
+int lgcn_score_topk(const float *user_emb, const float *item_emb, int64_t num_items,
+                    int64_t u_begin, int64_t u_end, int normalize, const int64_t *excl_ptr,
+                    const int32_t *excl_idx, int k, int32_t *topk_idx, float *topk_val,
+                    void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGCN_B200_H */

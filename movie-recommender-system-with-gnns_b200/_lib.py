@@ -1,0 +1,234 @@
+"""ctypes binding of csrc/liblgcn_b200.so (the C ABI declared in include/lgcn_b200.h).
+
+PyTorch is used here only for device memory and streams: every array the library reads or writes
+is a torch tensor allocated by this module, passed as a raw pointer.  There is NO fallback: if the
+shared library is missing, or a tensor is not on a CUDA device, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_int32, c_int64,
+                    c_size_t, c_uint8, c_void_p)
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liblgcn_b200.so")
+
+DIM = 64
+ROW_SPLIT = 512
+PARTIAL_STRIDE = 80
+
+EXPORTS = [
+    "lgcn_last_error", "lgcn_version", "lgcn_graph_sizes_query", "lgcn_graph_build",
+    "lgcn_propagate_fwd", "lgcn_propagate_bwd", "lgcn_bpr_fwd_bwd", "lgcn_step_begin",
+    "lgcn_clip_adam", "lgcn_train_step", "lgcn_eval_loss", "lgcn_partition_metis",
+    "lgcn_cluster_extract_workspace_bytes", "lgcn_cluster_extract", "lgcn_score_topk",
+    "lgcn_spmm", "lgcn_bpr_rows",
+]
+
+
+class LgcnError(RuntimeError):
+    pass
+
+
+class CTask(Structure):
+    _fields_ = [(n, c_int32) for n in ("row", "begin", "end", "slot", "part", "nparts", "pad0", "pad1")]
+
+
+class CGraph(Structure):
+    _fields_ = [
+        ("num_nodes", c_int32), ("num_users", c_int32), ("num_edges", c_int64), ("num_triplets", c_int64),
+        ("in_ptr", c_void_p), ("in_nbr", c_void_p), ("in_trip", c_void_p),
+        ("out_ptr", c_void_p), ("out_nbr", c_void_p), ("out_trip", c_void_p),
+        ("dis", c_void_p), ("active", c_void_p), ("in_tasks", c_void_p), ("out_tasks", c_void_p),
+        ("n_in_tasks", c_int32), ("n_out_tasks", c_int32),
+        ("n_in_user_tasks", c_int32), ("n_out_user_tasks", c_int32),
+        ("n_in_slots", c_int32), ("n_out_slots", c_int32),
+        ("partials", c_void_p), ("slot_counters", c_void_p),
+        ("num_active", c_int32), ("pad", c_int32),
+    ]
+
+
+class CGraphSizes(Structure):
+    _fields_ = [(n, c_size_t) for n in ("ptr_bytes", "nbr_bytes", "dis_bytes", "active_bytes", "task_bytes",
+                                        "partial_bytes", "counter_bytes", "workspace_bytes")]
+
+
+class CAdam(Structure):
+    _fields_ = [("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
+                ("max_norm", c_float), ("pad", c_int32), ("step", c_void_p), ("m", c_void_p), ("v", c_void_p)]
+
+
+class CStepBuffers(Structure):
+    _fields_ = [("final_emb", c_void_p), ("rnorm", c_void_p), ("grad_final", c_void_p), ("grad_e0", c_void_p),
+                ("work", c_void_p), ("work_bytes", c_size_t), ("neg_count", c_void_p),
+                ("trip_scratch", c_void_p), ("accum", c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LgcnError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                        "g.build()'` -- this package has no CPU or PyTorch fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    L.lgcn_last_error.restype = c_char_p
+    L.lgcn_version.restype = c_int
+    L.lgcn_graph_sizes_query.argtypes = [c_int64, c_int64, POINTER(CGraphSizes)]
+    L.lgcn_graph_build.argtypes = [c_void_p, c_int64, c_int64, c_int64, POINTER(CGraph), c_void_p, c_size_t, c_void_p]
+    L.lgcn_propagate_fwd.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_size_t, c_void_p]
+    L.lgcn_propagate_bwd.argtypes = [POINTER(CGraph), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float,
+                                     c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.lgcn_bpr_fwd_bwd.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]
+    L.lgcn_step_begin.argtypes = [POINTER(CAdam), c_void_p, c_void_p]
+    L.lgcn_clip_adam.argtypes = [POINTER(CAdam), c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                 c_float, c_void_p, c_void_p]
+    L.lgcn_train_step.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int, c_void_p, c_float, POINTER(CAdam),
+                                  POINTER(CStepBuffers), c_void_p, c_void_p]
+    L.lgcn_eval_loss.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int, c_void_p, c_float,
+                                 POINTER(CStepBuffers), c_void_p, c_void_p]
+    L.lgcn_partition_metis.argtypes = [c_int64, c_void_p, c_void_p, c_int64, c_void_p]
+    L.lgcn_cluster_extract_workspace_bytes.argtypes = [c_int64, c_int64, c_int64]
+    L.lgcn_cluster_extract_workspace_bytes.restype = c_size_t
+    L.lgcn_cluster_extract.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                       c_size_t, c_void_p]
+    L.lgcn_score_topk.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int,
+                                  c_void_p, c_void_p, c_void_p]
+    L.lgcn_spmm.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int, c_void_p]
+    L.lgcn_bpr_rows.argtypes = [c_void_p] * 6 + [c_int64, c_float, c_void_p, c_void_p, c_void_p] + [c_void_p] * 6 + [c_void_p]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("lgcn_last_error", "lgcn_cluster_extract_workspace_bytes"):
+            fn.restype = c_int
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise LgcnError(f"lgcn error {rc}: {lib().lgcn_last_error().decode()}")
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not t.is_cuda:
+        raise LgcnError(f"{name} must be a CUDA tensor (got {t.device}); this package has no CPU path")
+    if dtype is not None and t.dtype != dtype:
+        raise LgcnError(f"{name} must be {dtype} (got {t.dtype})")
+    return t
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Graph:
+    """Device-resident CSR pair + normalisation + warp task lists for one edge list (K0).
+
+    Built once per ``edge_index`` tensor and cached by callers; owns every array as a torch
+    tensor and exposes the C struct the kernels take."""
+
+    def __init__(self, edge_index: torch.Tensor, num_users: int, num_items: int):
+        require_cuda(edge_index, "edge_index", torch.int64)
+        if edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise LgcnError(f"edge_index must be [2,E], got {tuple(edge_index.shape)}")
+        ei = edge_index.contiguous()
+        dev = ei.device
+        n, e = num_users + num_items, ei.size(1)
+        L = lib()
+        sz = CGraphSizes()
+        check(L.lgcn_graph_sizes_query(n, e, byref(sz)))
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.device = dev
+        self.num_users, self.num_items, self.num_nodes, self.num_edges = num_users, num_items, n, e
+        e1 = max(e, 1)
+        self.in_ptr = torch.empty(n + 1, **i32)
+        self.out_ptr = torch.empty(n + 1, **i32)
+        self.in_nbr, self.in_trip = torch.empty(e1, **i32), torch.empty(e1, **i32)
+        self.out_nbr, self.out_trip = torch.empty(e1, **i32), torch.empty(e1, **i32)
+        self.dis = torch.empty(n, dtype=torch.float32, device=dev)
+        self.active = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.in_tasks = torch.empty(sz.task_bytes // 4, **i32)
+        self.out_tasks = torch.empty(sz.task_bytes // 4, **i32)
+        self.partials = torch.empty(sz.partial_bytes // 4, dtype=torch.float32, device=dev)
+        self.slot_counters = torch.empty(sz.counter_bytes // 4, **i32)
+        ws = torch.empty(sz.workspace_bytes, dtype=torch.uint8, device=dev)
+        c = CGraph()
+        c.in_ptr, c.in_nbr, c.in_trip = self.in_ptr.data_ptr(), self.in_nbr.data_ptr(), self.in_trip.data_ptr()
+        c.out_ptr, c.out_nbr, c.out_trip = self.out_ptr.data_ptr(), self.out_nbr.data_ptr(), self.out_trip.data_ptr()
+        c.dis, c.active = self.dis.data_ptr(), self.active.data_ptr()
+        c.in_tasks, c.out_tasks = self.in_tasks.data_ptr(), self.out_tasks.data_ptr()
+        c.partials, c.slot_counters = self.partials.data_ptr(), self.slot_counters.data_ptr()
+        check(L.lgcn_graph_build(ei.data_ptr(), e, n, num_users, byref(c), ws.data_ptr(), ws.numel(),
+                                 stream_ptr(dev)))
+        del ws
+        # shrink the over-allocated lists to what the build actually produced
+        self.in_tasks = self.in_tasks[: max(c.n_in_tasks, 1) * 8].clone()
+        self.out_tasks = self.out_tasks[: max(c.n_out_tasks, 1) * 8].clone()
+        nslots = max(c.n_in_slots, c.n_out_slots, 1)
+        self.partials = torch.empty(nslots * PARTIAL_STRIDE, dtype=torch.float32, device=dev)
+        self.slot_counters = torch.zeros(nslots, **i32)
+        c.in_tasks, c.out_tasks = self.in_tasks.data_ptr(), self.out_tasks.data_ptr()
+        c.partials, c.slot_counters = self.partials.data_ptr(), self.slot_counters.data_ptr()
+        self.c = c
+        self.num_triplets = int(c.num_triplets)
+        self.num_active = int(c.num_active)
+
+    @property
+    def ref(self):
+        return byref(self.c)
+
+    # integer views used by the bit-exact parity tests
+    def in_degree(self) -> torch.Tensor:
+        return (self.in_ptr[1:] - self.in_ptr[:-1]).to(torch.int64)
+
+    def out_degree(self) -> torch.Tensor:
+        return (self.out_ptr[1:] - self.out_ptr[:-1]).to(torch.int64)
+
+
+class StepBuffers:
+    """Scratch for one forward/backward pass (reused across steps; sized for the largest P seen)."""
+
+    def __init__(self, num_nodes: int, num_items: int, num_layers: int, device):
+        f32 = dict(dtype=torch.float32, device=device)
+        self.num_nodes, self.num_items, self.device = num_nodes, num_items, device
+        self.final_emb = torch.empty(num_nodes, DIM, **f32)
+        self.rnorm = torch.empty(num_nodes, **f32)
+        self.grad_final = torch.empty(num_nodes, DIM, **f32)
+        self.grad_e0 = torch.empty(num_nodes, DIM, **f32)
+        self.work = torch.empty(max(num_layers - 1, 2) * num_nodes * DIM, **f32)
+        self.neg_count = torch.zeros(num_items, dtype=torch.int32, device=device)
+        self.accum = torch.zeros(4, dtype=torch.float64, device=device)
+        self.trip_scratch = torch.empty(2, **f32)
+        self.c = CStepBuffers()
+        self._fill()
+
+    def _fill(self):
+        c = self.c
+        c.final_emb, c.rnorm = self.final_emb.data_ptr(), self.rnorm.data_ptr()
+        c.grad_final, c.grad_e0 = self.grad_final.data_ptr(), self.grad_e0.data_ptr()
+        c.work, c.work_bytes = self.work.data_ptr(), self.work.numel() * 4
+        c.neg_count, c.accum = self.neg_count.data_ptr(), self.accum.data_ptr()
+        c.trip_scratch = self.trip_scratch.data_ptr()
+
+    def ensure_triplets(self, p: int):
+        if self.trip_scratch.numel() < 2 * p:
+            self.trip_scratch = torch.empty(2 * p, dtype=torch.float32, device=self.device)
+            self._fill()
+
+    @property
+    def ref(self):
+        return byref(self.c)

@@ -1,0 +1,85 @@
+// K6: clip_grad_norm_(max_norm=1) + dense Adam over both embedding tables, one streaming pass.
+//
+// Replaces torch.nn.utils.clip_grad_norm_(model.parameters(), 1) and optimizer.step()
+// (/root/reference/utils/train_test.py:95-96; Adam(lr=1e-3) created at :236).  The update is
+// torch.optim.Adam's (amsgrad=False, weight_decay=0, maximize=False):
+//     m = m + (1-b1) (g - m);  v = b2 v + (1-b2) g^2
+//     p = p - (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// and it is DENSE on purpose: rows with zero gradient still move through their momentum
+// (SURVEY.md App. B #11).  HBM-streaming kernel: 4 reads + 3 writes of N*256 B.
+#include "common.cuh"
+#include <math.h>
+
+namespace lgcn {
+
+__global__ void step_begin_kernel(int64_t *step, double *accum) {
+    if (step) step[0] += 1;
+    accum[0] = 0.0; accum[1] = 0.0; accum[2] = 0.0; accum[3] = 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(float4 *__restrict__ user_w, float4 *__restrict__ item_w, size_t user_vec, size_t total_vec,
+                 const float4 *__restrict__ grad, float4 *__restrict__ m, float4 *__restrict__ v,
+                 const double *__restrict__ accum, const int64_t *__restrict__ step, float lr, float beta1,
+                 float beta2, float eps, float max_norm, int64_t P, float coeff, float *loss_out) {
+    // per-thread scalars (same value in every thread; cheap next to the streaming loop)
+    const double t = (double)step[0];
+    const double bc1 = 1.0 - pow((double)beta1, t);
+    const double bc2 = 1.0 - pow((double)beta2, t);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float total_norm = (float)sqrt(accum[2]);
+    float clip = max_norm > 0.f ? max_norm / (total_norm + 1e-6f) : 1.0f;   // max_norm <= 0: no clipping
+    clip = fminf(clip, 1.0f);
+    const float w1 = 1.0f - beta1, w2 = 1.0f - beta2;
+    if (loss_out && blockIdx.x == 0 && threadIdx.x == 0) {
+        const double p = (double)P;
+        loss_out[0] = (float)(-accum[0] / (10.0 * p) + (double)coeff * accum[1] / (64.0 * p));
+    }
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+        float4 *pp = i < user_vec ? user_w + i : item_w + (i - user_vec);
+        const float4 g4 = __ldcs(grad + i);
+        float4 p4 = *pp, m4 = m[i], v4 = v[i];
+        float *p = &p4.x, *mm = &m4.x, *vv = &v4.x;
+        const float *g = &g4.x;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float gc = g[c] * clip;
+            mm[c] = mm[c] + w1 * (gc - mm[c]);                    // exp_avg.lerp_(grad, 1-beta1)
+            vv[c] = vv[c] * beta2 + w2 * gc * gc;                 // mul_(beta2).addcmul_(g, g, 1-beta2)
+            const float denom = sqrtf(vv[c]) / bc2_sqrt + eps;
+            p[c] = p[c] - step_size * (mm[c] / denom);            // addcdiv_(m, denom, -step_size)
+        }
+        *pp = p4; m[i] = m4; v[i] = v4;
+    }
+}
+
+}  // namespace lgcn
+
+extern "C" int lgcn_step_begin(const lgcn_adam *opt, double *accum, void *stream) {
+    LGCN_REQUIRE(accum, LGCN_E_INVALID, "step_begin: null accum");
+    lgcn::step_begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(opt ? opt->step : nullptr, accum);
+    LGCN_LAUNCH_CHECK();
+    return LGCN_OK;
+}
+
+extern "C" int lgcn_clip_adam(const lgcn_adam *opt, float *user_w, float *item_w, int64_t num_users,
+                              int64_t num_items, const float *grad, const double *accum,
+                              int64_t num_triplets, float bpr_coeff, float *loss_out, void *stream) {
+    LGCN_REQUIRE(opt && user_w && item_w && grad && accum && opt->m && opt->v && opt->step, LGCN_E_INVALID,
+                 "clip_adam: null argument");
+    const size_t user_vec = (size_t)num_users * lgcn::D4, total = (size_t)(num_users + num_items) * lgcn::D4;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (int64_t)((total + 255) / 256);
+    const int grid = (int)(want < (int64_t)sms * 8 ? (want > 0 ? want : 1) : (int64_t)sms * 8);
+    lgcn::clip_adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4 *>(user_w), reinterpret_cast<float4 *>(item_w), user_vec, total,
+        reinterpret_cast<const float4 *>(grad), reinterpret_cast<float4 *>(opt->m),
+        reinterpret_cast<float4 *>(opt->v), accum, opt->step, opt->lr, opt->beta1, opt->beta2, opt->eps,
+        opt->max_norm, num_triplets, bpr_coeff, loss_out);
+    LGCN_LAUNCH_CHECK();
+    return LGCN_OK;
+}

@@ -1,0 +1,84 @@
+// Shared device/host helpers for the sm_100a LightGCN kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "lgcn_b200.h"
+
+namespace lgcn {
+
+constexpr int D = LGCN_DIM;                 // 64 fp32 = 256 B per embedding row
+constexpr int D4 = D / 4;                   // float4 per row (one per lane of a half-warp)
+constexpr int WARPS_PER_CTA = 8;
+constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+constexpr int PARTIAL_STRIDE = 80;          // floats per partial slot: 64 + scalar, 64 B aligned
+constexpr unsigned FULL = 0xffffffffu;
+
+void set_error(const char *fmt, ...);
+
+#define LGCN_REQUIRE(cond, code, ...)                                                         \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            ::lgcn::set_error(__VA_ARGS__);                                                   \
+            return (code);                                                                    \
+        }                                                                                     \
+    } while (0)
+
+#define LGCN_CUDA(expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ::lgcn::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr,                    \
+                              cudaGetErrorString(_e));                                        \
+            return LGCN_E_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+#define LGCN_LAUNCH_CHECK() LGCN_CUDA(cudaGetLastError())
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// The embedding table e0 = cat(user_embedding.weight, item_embedding.weight)
+// (models/light_gcn.py:29) without materialising the concatenation.
+struct Table {
+    const float *user;
+    const float *item;
+    int num_users;
+    __device__ __forceinline__ const float4 *row4(int r) const {
+        const float *p = r < num_users ? user + (size_t)r * D : item + (size_t)(r - num_users) * D;
+        return reinterpret_cast<const float4 *>(p);
+    }
+};
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4add(float4 &a, const float4 &b) {
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+}
+__device__ __forceinline__ void f4fma(float4 &a, float s, const float4 &b) {
+    a.x = fmaf(s, b.x, a.x); a.y = fmaf(s, b.y, a.y); a.z = fmaf(s, b.z, a.z); a.w = fmaf(s, b.w, a.w);
+}
+__device__ __forceinline__ float4 f4scale(float s, const float4 &b) {
+    return make_float4(s * b.x, s * b.y, s * b.z, s * b.w);
+}
+__device__ __forceinline__ float f4dot(const float4 &a, const float4 &b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+// sum over the 16 lanes of a half-warp (xor 8,4,2,1 never crosses the half boundary)
+__device__ __forceinline__ float half_sum(float v) {
+    v += __shfl_xor_sync(FULL, v, 8);
+    v += __shfl_xor_sync(FULL, v, 4);
+    v += __shfl_xor_sync(FULL, v, 2);
+    v += __shfl_xor_sync(FULL, v, 1);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+    v += __shfl_xor_sync(FULL, v, 16);
+    return half_sum(v);
+}
+__device__ __forceinline__ float4 f4shfl_xor16(const float4 &a) {
+    return make_float4(__shfl_xor_sync(FULL, a.x, 16), __shfl_xor_sync(FULL, a.y, 16),
+                       __shfl_xor_sync(FULL, a.z, 16), __shfl_xor_sync(FULL, a.w, 16));
+}
+
+}  // namespace lgcn

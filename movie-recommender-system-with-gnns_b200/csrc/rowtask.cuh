@@ -1,0 +1,120 @@
+// Warp-per-row-task driver shared by the SpMM (forward / backward) and BPR kernels.
+//
+// One warp owns one lgcn_task = a run of at most LGCN_ROW_SPLIT edges of one CSR row.  The warp
+// is split in two half-warps; each half-warp gathers one neighbour row at a time with 16
+// 128-bit loads (16 lanes x float4 = the 256 B embedding row), UNROLL rows in flight per
+// half-warp, so a warp keeps 2*UNROLL independent 256 B gathers outstanding.  Lane l (mod 16)
+// accumulates columns 4l..4l+3; the two halves are combined with one xor-16 shuffle.
+//
+// Rows longer than LGCN_ROW_SPLIT are cut into several tasks.  Each writes its partial sum to a
+// slot; the task that arrives last (atomic counter per row) re-reads all partials IN SLOT ORDER
+// and runs the row epilogue, so the result is deterministic and no float atomics are used.
+//
+// An Op provides:
+//   accumulate(row, begin, end, lane, float4& acc, float& sc, float& ex0, float& ex1)
+//                                                               edge loop (acc: this lane's 4
+//                                                               columns; sc: per-lane scalar)
+//   epilogue(row, lane, acc, sc, float& ex0, float& ex1)        acc/sc are full-row sums,
+//                                                               identical in both half-warps
+//   static constexpr bool kExtras; double *extra0, *extra1      optional per-CTA reduced sums
+#pragma once
+#include "common.cuh"
+
+namespace lgcn {
+
+constexpr int UNROLL = 8;   // neighbour rows in flight per half-warp (SpMM)
+
+// Iterate the edges [begin,end) of a CSR row.  `fetch(lane_edge_index)` is evaluated once per
+// edge by the lane that owns it within a 32-edge chunk and returns a small POD that is then
+// broadcast to the half-warp that processes the edge; `body(u, item)` loads, `apply(u, item)`
+// consumes.  Kept as a macro-free template so every user gets the same load batching.
+template <class Item, int kUnroll = UNROLL, class Fetch, class Load, class Apply>
+__device__ __forceinline__ void for_each_edge(int begin, int end, int lane, Fetch fetch, Load load,
+                                              Apply apply) {
+    const int half = lane >> 4;
+    for (int base = begin; base < end; base += 32) {
+        const int n = min(32, end - base);
+        Item mine = fetch(lane < n ? base + lane : -1);
+#pragma unroll
+        for (int j = 0; j < 32; j += 2 * kUnroll) {
+            if (j >= n) break;                       // warp-uniform
+            Item it[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                it[u] = mine.shfl(j + 2 * u + half);
+                load(u, it[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) apply(u, it[u]);
+        }
+    }
+}
+
+template <class Op>
+__global__ void __launch_bounds__(CTA_THREADS)
+rowtask_kernel(Op op, const lgcn_task *__restrict__ tasks, int task_begin, int task_end,
+               float *__restrict__ partials, int *__restrict__ counters) {
+    const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
+    const int tix = task_begin + blockIdx.x * WARPS_PER_CTA + wid;
+    float ex0 = 0.f, ex1 = 0.f;
+    if (tix < task_end) {
+        const int4 ta = __ldg(reinterpret_cast<const int4 *>(tasks + tix));
+        const int4 tb = __ldg(reinterpret_cast<const int4 *>(tasks + tix) + 1);
+        const int row = ta.x, begin = ta.y, end = ta.z, slot = ta.w, part = tb.x, nparts = tb.y;
+        float4 acc = f4zero();
+        float sc = 0.f;
+        op.accumulate(row, begin, end, lane, acc, sc, ex0, ex1);
+        f4add(acc, f4shfl_xor16(acc));
+        sc = warp_sum(sc);
+        bool run_epilogue = slot < 0;
+        if (slot >= 0) {
+            float *p = partials + (size_t)slot * PARTIAL_STRIDE;
+            if (lane < 16) reinterpret_cast<float4 *>(p)[lane] = acc;
+            if (lane == 16) p[D] = sc;
+            __threadfence();
+            const int first = slot - part;
+            int old = 0;
+            if (lane == 0) old = atomicAdd(counters + first, 1);
+            old = __shfl_sync(FULL, old, 0);
+            if (old == nparts - 1) {                 // last arriver reduces in slot order
+                __threadfence();
+                acc = f4zero();
+                sc = 0.f;
+                for (int i = 0; i < nparts; ++i) {
+                    const float *q = partials + (size_t)(first + i) * PARTIAL_STRIDE;
+                    f4add(acc, __ldcg(reinterpret_cast<const float4 *>(q) + (lane & 15)));
+                    sc += __ldcg(q + D);
+                }
+                if (lane == 0) counters[first] = 0;  // ready for the next launch
+                run_epilogue = true;
+            }
+        }
+        if (run_epilogue) op.epilogue(row, lane, acc, sc, ex0, ex1);
+    }
+    if constexpr (Op::kExtras) {
+        __shared__ float s_ex[WARPS_PER_CTA][2];
+        if (lane == 0) { s_ex[wid][0] = ex0; s_ex[wid][1] = ex1; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int w = 0; w < WARPS_PER_CTA; ++w) { a += s_ex[w][0]; b += s_ex[w][1]; }
+            if (op.extra0 && a != 0.0) atomicAdd(op.extra0, a);
+            if (op.extra1 && b != 0.0) atomicAdd(op.extra1, b);
+        }
+    }
+}
+
+template <class Op>
+static inline cudaError_t launch_rowtasks(const Op &op, const lgcn_task *tasks, int task_begin,
+                                          int task_end, float *partials, int *counters,
+                                          cudaStream_t stream) {
+    const int n = task_end - task_begin;
+    if (n <= 0) return cudaSuccess;
+    rowtask_kernel<Op><<<cdiv(n, WARPS_PER_CTA), CTA_THREADS, 0, stream>>>(op, tasks, task_begin,
+                                                                           task_end, partials, counters);
+    return cudaGetLastError();
+}
+
+}  // namespace lgcn

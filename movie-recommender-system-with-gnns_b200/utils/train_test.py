@@ -1,0 +1,243 @@
+"""Training / evaluation loop with the reference's function signatures
+(/root/reference/utils/train_test.py:18-256) running on the sm_100a kernels.
+
+Two ways through ``train``:
+  * ``FusedAdam`` optimiser (what ``train_model`` creates): ONE C-ABI call per batch
+    (``lgcn_train_step`` = forward, BPR loss, backward, clip, Adam -- utils/train_test.py:88-96),
+    no per-batch host sync; the per-batch losses are read back once per epoch.
+  * any ``torch.optim`` optimiser: the reference's own sequence (compute_embeddings -> bpr_loss ->
+    backward -> clip_grad_norm_ -> step) with the model forward/backward and the loss on the
+    kernels via autograd.
+"""
+from __future__ import annotations
+
+from ctypes import byref
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .._lib import CAdam, DIM, LgcnError, StepBuffers, check, lib, require_cuda, stream_ptr
+from .helpers import get_triplets_indices, sample_negative
+
+
+# ----------------------------------------------------------------------------------------------
+# bpr_loss on gathered rows (drop-in signature)
+# ----------------------------------------------------------------------------------------------
+
+class _BprRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, uf, u0, pf, p0, nf, n0, coeff):
+        ts = [require_cuda(t, "bpr_loss input", torch.float32).contiguous() for t in (uf, u0, pf, p0, nf, n0)]
+        p = ts[0].size(0)
+        if any(t.shape != (p, DIM) for t in ts):
+            raise LgcnError(f"bpr_loss expects six [P,{DIM}] tensors")
+        dev = ts[0].device
+        accum = torch.empty(2, dtype=torch.float64, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        if p == 0:                       # mean over an empty set, as in the reference (NaN)
+            return loss.fill_(float("nan"))
+        check(lib().lgcn_bpr_rows(*[t.data_ptr() for t in ts], p, coeff, accum.data_ptr(), loss.data_ptr(), None,
+                                  None, None, None, None, None, None, stream_ptr(dev)))
+        ctx.save_for_backward(*ts)
+        ctx.coeff = coeff
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ts = ctx.saved_tensors
+        p, dev = ts[0].size(0), ts[0].device
+        gs = grad_out.to(torch.float32).contiguous()
+        grads = [torch.empty_like(t) for t in ts]
+        # order of the C signature: g_uf, g_u0, g_pf, g_p0, g_nf, g_n0  == order of the inputs
+        check(lib().lgcn_bpr_rows(*[t.data_ptr() for t in ts], p, ctx.coeff, None, None, gs.data_ptr(),
+                                  *[g.data_ptr() for g in grads], stream_ptr(dev)))
+        return (*grads, None)
+
+
+def bpr_loss(emb_users_final: torch.Tensor, emb_users: torch.Tensor,
+             emb_pos_items_final: torch.Tensor, emb_pos_items: torch.Tensor,
+             emb_neg_items_final: torch.Tensor, emb_neg_items: torch.Tensor,
+             bpr_coeff: float = 5e-3) -> torch.Tensor:
+    """-mean(softplus(10 (cos+ - cos-)))/10 + bpr_coeff * mean(u0^2 + p0^2 + n0^2)
+    (utils/train_test.py:18-51), one fused kernel, differentiable w.r.t. all six inputs."""
+    return _BprRows.apply(emb_users_final, emb_users, emb_pos_items_final, emb_pos_items,
+                          emb_neg_items_final, emb_neg_items, float(bpr_coeff))
+
+
+def normalize_embedding(emb: torch.Tensor) -> torch.Tensor:
+    """Row-wise L2 normalisation without epsilon (utils/train_test.py:53-64)."""
+    return emb / torch.norm(emb, p=2, dim=1, keepdim=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# fused optimiser state
+# ----------------------------------------------------------------------------------------------
+
+class FusedAdam:
+    """Adam(lr, betas=(0.9, 0.999), eps=1e-8) over both embedding tables preceded by
+    clip_grad_norm_(max_norm) -- utils/train_test.py:95-96,236 -- as state for the fused step.
+    exp_avg / exp_avg_sq are flat [N,64] tensors; the step counter lives on the device so that a
+    training step needs no host round trip."""
+
+    def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0):
+        w = model.user_embedding.weight
+        require_cuda(w, "model parameters", torch.float32)
+        self.model = model
+        n = model.num_users + model.num_items
+        self.exp_avg = torch.zeros(n, DIM, dtype=torch.float32, device=w.device)
+        self.exp_avg_sq = torch.zeros(n, DIM, dtype=torch.float32, device=w.device)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=w.device)
+        self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
+        self.buffers = StepBuffers(n, model.num_items, model.num_layers, w.device)
+        self.c = CAdam()
+        self._fill()
+
+    def _fill(self):
+        c = self.c
+        c.lr, c.beta1, c.beta2, c.eps, c.max_norm = self.lr, self.betas[0], self.betas[1], self.eps, self.max_norm
+        c.step, c.m, c.v = self.step_count.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+
+    def zero_grad(self):
+        pass
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,
+                "lr": self.lr, "betas": self.betas, "eps": self.eps, "max_norm": self.max_norm}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"]); self.step_count.copy_(sd["step"])
+        self.lr, self.betas, self.eps, self.max_norm = sd["lr"], tuple(sd["betas"]), sd["eps"], sd["max_norm"]
+        self._fill()
+
+
+def train_step(model, optimizer: FusedAdam, edge_index: torch.Tensor, neg: Optional[torch.Tensor] = None,
+               loss_out: Optional[torch.Tensor] = None, bpr_coeff: float = 5e-3) -> torch.Tensor:
+    """The loop body utils/train_test.py:88-96 for one batch as one C-ABI call.  ``neg`` defaults to
+    the reference's sampling (utils/helpers.py:79-80).  Returns a 0-dim DEVICE tensor (no sync)."""
+    g = model.graph(edge_index)
+    dev = edge_index.device
+    if g.num_triplets == 0:
+        raise LgcnError("batch has no user->movie edge: the reference's loss is NaN here (SURVEY App. B #13)")
+    if neg is None:
+        neg = torch.randint(0, model.num_items, (g.num_triplets,), device=dev)
+    require_cuda(neg, "neg", torch.int64)
+    if neg.numel() != g.num_triplets:
+        raise LgcnError(f"neg has {neg.numel()} entries, the batch has {g.num_triplets} user->movie edges")
+    if loss_out is None:
+        loss_out = torch.empty(1, dtype=torch.float32, device=dev)
+    uw, iw = model.user_embedding.weight, model.item_embedding.weight
+    if not (uw.is_contiguous() and iw.is_contiguous()):
+        raise LgcnError("embedding weights must be contiguous")
+    optimizer.buffers.ensure_triplets(g.num_triplets)
+    check(lib().lgcn_train_step(g.ref, uw.data_ptr(), iw.data_ptr(), model.num_layers, neg.contiguous().data_ptr(),
+                                bpr_coeff, byref(optimizer.c), optimizer.buffers.ref, loss_out.data_ptr(),
+                                stream_ptr(dev)))
+    return loss_out
+
+
+def train(model: torch.nn.Module, optimizer, train_loader, device: torch.device) -> float:
+    """One epoch (utils/train_test.py:66-103): edge-count-weighted mean of the batch losses."""
+    model.train()
+    if isinstance(optimizer, FusedAdam):
+        batches = [b.to(device) for b in train_loader]
+        batches = [b for b in batches if b.edge_index.shape[1] > 0 and model.graph(b.edge_index).num_triplets > 0]
+        if not batches:
+            return float("nan")
+        losses = torch.empty(len(batches), dtype=torch.float32, device=device)
+        for i, batch in enumerate(batches):
+            train_step(model, optimizer, batch.edge_index, loss_out=losses[i:i + 1])
+        w = torch.tensor([b.edge_index.shape[1] for b in batches], dtype=torch.float64)
+        return float((losses.double().cpu() * w).sum() / w.sum())        # the epoch's only sync
+
+    total_loss, total_w = 0.0, 0
+    for batch in train_loader:
+        batch = batch.to(device)
+        optimizer.zero_grad()
+        embs = compute_embeddings(model, batch, device)
+        train_loss = bpr_loss(*embs)
+        train_loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1)
+        optimizer.step()
+        w = batch.edge_index.shape[1]
+        total_w += w
+        total_loss += train_loss.item() * w
+    return total_loss / total_w
+
+
+def compute_embeddings(model: torch.nn.Module, data, device: torch.device) -> Tuple[torch.Tensor, ...]:
+    """Final/initial rows for (user, pos, neg) of every user->movie edge (utils/train_test.py:105-134)."""
+    final_user, final_item = model(data.edge_index)
+    init_user, init_item = model.user_embedding.weight, model.item_embedding.weight
+    u, p, n = get_triplets_indices(data.edge_index, model.num_users, model.num_items, device)
+    return final_user[u], init_user[u], final_item[p], init_item[p], final_item[n], init_item[n]
+
+
+def eval_loss(model, edge_index: torch.Tensor, neg: torch.Tensor, buffers: Optional[StepBuffers] = None,
+              bpr_coeff: float = 5e-3) -> torch.Tensor:
+    """Loss of evaluate() without materialising the six gathers (utils/train_test.py:153-156)."""
+    g = model.graph(edge_index)
+    dev = edge_index.device
+    if buffers is None:
+        buffers = StepBuffers(g.num_nodes, model.num_items, model.num_layers, dev)
+    out = torch.empty(1, dtype=torch.float32, device=dev)
+    check(lib().lgcn_eval_loss(g.ref, model.user_embedding.weight.data_ptr(), model.item_embedding.weight.data_ptr(),
+                               model.num_layers, neg.contiguous().data_ptr(), bpr_coeff, buffers.ref, out.data_ptr(),
+                               stream_ptr(dev)))
+    return out
+
+
+def evaluate(model: torch.nn.Module, test_data, device: torch.device, top_k: int = 100) -> Tuple[float, float]:
+    """Loss over the given edges + the reference's sampled recall on LAYER-0 rows
+    (utils/train_test.py:136-163)."""
+    model.eval()
+    with torch.no_grad():
+        test_data = test_data.to(device)
+        u, p, n = get_triplets_indices(test_data.edge_index, model.num_users, model.num_items, device)
+        test_loss = eval_loss(model, test_data.edge_index, n).item()
+        uw, iw = model.user_embedding.weight, model.item_embedding.weight
+        recall_at_k = compute_recall_at_k((uw[u], iw[p], iw[n]), k=top_k)
+    return test_loss, recall_at_k
+
+
+def compute_recall_at_k(embs, k: int = 20, num_samples: int = 10, sample_size: int = 100,
+                        sampled: Optional[Sequence[np.ndarray]] = None) -> float:
+    """The reference's sampled Recall@k (utils/train_test.py:165-212), definition preserved: the
+    candidate pool is the [pos; neg] rows, a hit is any top-k column < P, the denominator is P.
+    Scoring + top-k run in the fused kernel (no 100 x 2P score matrix).  ``sampled`` lets a test
+    supply the np.random.choice draws (:187)."""
+    from .recommend import score_topk
+    user_embs, pos_item_embs, neg_item_embs = embs
+    p = pos_item_embs.size(0)
+    cand = torch.cat((pos_item_embs, neg_item_embs)).contiguous()
+    num_users = user_embs.size(0)
+    total = 0.0
+    for s in range(num_samples):
+        idx = sampled[s] if sampled is not None else np.random.choice(num_users, sample_size, replace=False)
+        rows = user_embs[torch.as_tensor(idx, device=user_embs.device)].contiguous()
+        top_idx, _ = score_topk(rows, cand, k, normalize=True)
+        hits = (top_idx < p).sum(dim=1).to(torch.float32)
+        total += (hits / p).mean().item()
+    return total / num_samples
+
+
+def train_model(model: torch.nn.Module, train_loader, val_data, test_data, device: torch.device,
+                epochs: int = 1, lr: float = 0.001):
+    """utils/train_test.py:214-256 (Adam lr, best-val-recall checkpoint to best_model.pth)."""
+    hist_train_loss, hist_val_loss, hist_val_recall = [], [], []
+    optimizer = FusedAdam(model, lr=lr)
+    best_recall = 0
+    for epoch in range(epochs):
+        loss = train(model, optimizer, train_loader, device)
+        val_loss, recall_at_k = evaluate(model, val_data, device)
+        hist_train_loss.append(loss)
+        hist_val_loss.append(val_loss)
+        hist_val_recall.append(recall_at_k)
+        print(f"Epoch: {epoch:03d}, Train Loss: {loss:.4f}, Val Loss: {val_loss:.4f}, "
+              f"Recall@k: {recall_at_k:.6f}, k=100")
+        if recall_at_k > best_recall:
+            best_recall = recall_at_k
+            torch.save(model.state_dict(), "best_model.pth")
+    test_loss, recall_at_k = evaluate(model, test_data, device)
+    print(f"Test Loss: {test_loss:.4f}, Recall@k: {recall_at_k:.6f}, k=100")
+    return model, hist_train_loss, hist_val_loss, hist_val_recall

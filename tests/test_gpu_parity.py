@@ -1,0 +1,315 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs, against the golden fixtures produced by the unmodified reference, and through
+size-independent properties.  Bars: integer structures bit-exact; fp32 tensors normwise 1e-5
+(max|d| <= 1e-5 max|ref|) against the fp64 oracle; post-optimiser weights per
+conftest.ADAM_STEP_ATOL."""
+import numpy as np
+import pytest
+import torch
+
+import lgcn_b200  # noqa: F401
+from conftest import ADAM_STEP_ATOL, max_abs, normwise
+from lgcn_b200 import _lib
+from lgcn_b200.data import synthetic
+from lgcn_b200.models.light_gcn import LGConv, LightGCN
+from lgcn_b200.utils import train_test as tt
+from lgcn_b200.utils.helpers import get_triplets_indices
+from oracle import pyg_restated as pyg
+from oracle import reference_path as ref
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = torch.device("cuda:0") if torch.cuda.is_available() else None
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _model(nu, ni, k, u0, i0):
+    m = LightGCN(nu, ni, num_layers=k).to(DEV)
+    with torch.no_grad():
+        m.user_embedding.weight.copy_(u0)
+        m.item_embedding.weight.copy_(i0)
+    return m
+
+
+def _case(shape, seed=0):
+    g = synthetic.make_graph(shape, seed=seed)
+    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, seed)
+    return g, g.edges("train"), synthetic.SHAPES[shape][3], u0, i0
+
+
+def _negs(train, nu, ni, seed):
+    gen = torch.Generator().manual_seed(seed)
+    return torch.randint(0, ni, (int((train[0] < nu).sum()),), generator=gen)
+
+
+# ---------------------------------------------------------------------------------------------
+# K0: CSR / degree / normalisation indexing -- bit-exact
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shape,shuffle", [("tiny", False), ("tiny", True), ("ml100k", False), ("ml1m", True)])
+def test_graph_build_bit_exact(shape, shuffle):
+    g, train, k, _, _ = _case(shape)
+    if shuffle:                                   # arbitrary edge order must keep a stable in-row order
+        perm = torch.randperm(train.shape[1], generator=torch.Generator().manual_seed(3))
+        train = train[:, perm].contiguous()
+    n = g.num_nodes
+    d = ref.degree_structs(train, n)
+    G = _lib.Graph(train.to(DEV), g.num_users, g.num_items)
+    assert torch.equal(G.in_ptr.cpu().long(), d["ptr_in"]) and torch.equal(G.out_ptr.cpu().long(), d["ptr_out"])
+    assert torch.equal(G.in_nbr.cpu().long()[: train.shape[1]], d["src_by_target"])
+    assert torch.equal(G.out_nbr.cpu().long()[: train.shape[1]], d["dst_by_source"])
+    assert torch.equal(G.in_degree().cpu(), d["in_deg"]) and torch.equal(G.out_degree().cpu(), d["out_deg"])
+    deg, dis, _ = pyg.gcn_norm(train, n, torch.float32)
+    assert float((G.dis.cpu() - dis).abs().max()) <= 1e-7          # 1 ulp of deg^-1/2
+    assert torch.equal(G.dis.cpu() == 0, deg == 0)
+    # triplet ids: rank among edges with source < U, in edge order
+    user, pos = ref.triplet_users_pos(train, g.num_users)
+    assert G.num_triplets == user.numel()
+    trip_of_edge = torch.cumsum((train[0] < g.num_users).long(), 0) - 1
+    ot = G.out_trip.cpu().long()[: train.shape[1]]
+    um = d["eid_by_source"][train[0][d["eid_by_source"]] < g.num_users]
+    assert torch.equal(ot[: um.numel()], trip_of_edge[um])
+    assert G.num_active == int(((d["in_deg"] > 0) | (d["out_deg"] > 0)).sum())
+    # task lists cover every edge of every active row exactly once
+    tasks = G.in_tasks.cpu().view(-1, 8)[: G.c.n_in_tasks]
+    assert int((tasks[:, 2] - tasks[:, 1]).sum()) == train.shape[1]
+    assert int((tasks[:, 2] - tasks[:, 1]).max()) <= _lib.ROW_SPLIT
+
+
+def test_graph_build_rejects_bad_input():
+    ei = torch.tensor([[0, 1], [1, 0]], device=DEV)            # user->user with U=2
+    with pytest.raises(_lib.LgcnError):
+        _lib.Graph(ei, 2, 2)
+    with pytest.raises(_lib.LgcnError):
+        _lib.Graph(torch.tensor([[0], [9]], device=DEV), 2, 2)  # id out of range
+    with pytest.raises(_lib.LgcnError):
+        _lib.Graph(torch.tensor([[0], [2]]), 2, 2)              # CPU tensor: no fallback
+
+
+# ---------------------------------------------------------------------------------------------
+# K1: forward
+# ---------------------------------------------------------------------------------------------
+
+def test_forward_smoke_graph_golden_and_closed_form(golden):
+    g = golden("smoke_matching.npz")
+    u0, i0 = _t(g["user_w"]), _t(g["item_w"])
+    m = _model(10, 15, 4, u0, i0)
+    uf, itf = m(_t(g["edge_index"]).to(DEV))
+    assert normwise(uf, _t(g["user_final"])) < TOL and normwise(itf, _t(g["item_final"])) < TOL
+    assert normwise(uf, (3 * u0 + 2 * i0[:10]) / 25) < TOL and normwise(itf[10:], i0[10:] / 25) < TOL
+    su, si = m.get_embeddings(torch.tensor([0, 1, 2]), torch.tensor([3, 4, 5, 6]))
+    assert torch.equal(su.cpu(), _t(g["sel_user"])) and torch.equal(si.cpu(), _t(g["sel_item"]))
+    with pytest.warns(UserWarning):
+        assert m.get_embeddings() == (None, None)
+    assert list(m.state_dict().keys()) == ["user_embedding.weight", "item_embedding.weight"]
+
+
+@pytest.mark.parametrize("name", ["tiny_step.npz", "ml100k_step.npz"])
+def test_forward_matches_reference_golden(golden, name):
+    gd = golden(name)
+    g, train, k, u0, i0 = _case(str(gd["shape"]))
+    s = int(gd["row_stride"])
+    m = _model(g.num_users, g.num_items, k, u0, i0)
+    uf, itf = m(train.to(DEV))
+    assert normwise(uf[::s], _t(gd["user_final"])) < TOL and normwise(itf[::s], _t(gd["item_final"])) < TOL
+    r64u, r64i = ref.forward(u0.double(), i0.double(), train, k)
+    assert normwise(uf, r64u) < TOL and normwise(itf, r64i) < TOL
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_forward_all_layer_counts_and_split_rows(k):
+    # ml1m shape has item rows of > 2,000 in-edges: exercises the split-row / last-arriver path
+    g, train, _, u0, i0 = _case("ml1m")
+    m = _model(g.num_users, g.num_items, k, u0, i0)
+    ei = train.to(DEV)
+    G = m.graph(ei)
+    assert G.c.n_in_slots > 0 and G.c.n_out_slots > 0
+    uf, itf = m(ei)
+    r64u, r64i = ref.forward(u0.double(), i0.double(), train, k)
+    assert normwise(uf, r64u) < TOL and normwise(itf, r64i) < TOL
+    uf2, itf2 = m(ei)                                             # owner-computes => bit-stable
+    assert torch.equal(uf, uf2) and torch.equal(itf, itf2)
+
+
+def test_forward_sparse_batch_isolated_nodes_and_zero_indegree_sources():
+    # a Cluster-GCN-like batch: few edges on the FULL table
+    g, train, k, u0, i0 = _case("ml100k")
+    sub = train[:, ::97].contiguous()
+    m = _model(g.num_users, g.num_items, k, u0, i0)
+    uf, itf = m(sub.to(DEV))
+    r64u, r64i = ref.forward(u0.double(), i0.double(), sub, k)
+    assert normwise(uf, r64u) < TOL and normwise(itf, r64i) < TOL
+    d = ref.degree_structs(sub, g.num_nodes)
+    iso = (d["in_deg"] == 0) & (d["out_deg"] == 0)
+    assert iso.any() and ((d["in_deg"] == 0) & (d["out_deg"] > 0)).any()
+    full = torch.cat([uf, itf]).cpu()
+    e0 = torch.cat([u0, i0])
+    assert normwise(full[iso], e0[iso] / (k + 1) ** 2) < 1e-6
+    # empty edge list: every layer is zero
+    uf, itf = m(torch.zeros(2, 0, dtype=torch.int64, device=DEV))
+    assert normwise(uf, u0 / (k + 1) ** 2) < 1e-6 and normwise(itf, i0 / (k + 1) ** 2) < 1e-6
+
+
+def test_lgconv_operator_and_adjoint():
+    g, train, k, u0, i0 = _case("tiny")
+    x = torch.cat([u0, i0])
+    conv = LGConv(g.num_users)
+    ei = train.to(DEV)
+    out = conv(x=x.to(DEV), edge_index=ei)
+    assert normwise(out, pyg.lgconv(x.double(), train)) < TOL
+    assert normwise(LGConv()(x=x.to(DEV), edge_index=ei), out) == 0.0      # boundary inferred
+    # <A x, y> == <x, A^T y>  (backward kernel is the exact adjoint of the forward one)
+    xg = x.to(DEV).requires_grad_(True)
+    y = torch.randn(x.shape, generator=torch.Generator().manual_seed(1)).to(DEV)
+    (conv(xg, ei) * y).sum().backward()
+    a = pyg.lgconv(x.double(), train)
+    xd = x.double().requires_grad_(True)
+    (pyg.lgconv(xd, train) * y.cpu().double()).sum().backward()
+    assert normwise(xg.grad, xd.grad) < TOL
+    # linearity
+    z = torch.randn(x.shape, generator=torch.Generator().manual_seed(2)).to(DEV)
+    lhs = conv(2.0 * x.to(DEV) + z, ei)
+    rhs = 2.0 * out + conv(z, ei)
+    assert normwise(lhs, rhs) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# K2/K3: loss and gradients (composed reference-style API, via autograd)
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["tiny_step.npz", "ml100k_step.npz"])
+def test_loss_and_grads_match_reference_golden(golden, name):
+    gd = golden(name)
+    g, train, k, u0, i0 = _case(str(gd["shape"]))
+    s = int(gd["row_stride"])
+    m = _model(g.num_users, g.num_items, k, u0, i0)
+    ei = train.to(DEV)
+    neg = _t(gd["neg"]).long()
+    user, pos, _ = get_triplets_indices(ei, g.num_users, g.num_items, DEV)
+    assert torch.equal(user.cpu()[::s], _t(gd["user"]).long()) and torch.equal(pos.cpu()[::s], _t(gd["pos"]).long())
+    uf, itf = m(ei)
+    uw, iw = m.user_embedding.weight, m.item_embedding.weight
+    n = neg.to(DEV)
+    loss = tt.bpr_loss(uf[user], uw[user], itf[pos], iw[pos], itf[n], iw[n])
+    loss.backward()
+    assert abs(float(loss) - float(gd["loss"])) < TOL * abs(float(gd["loss"]))
+    assert normwise(uw.grad[::s], _t(gd["grad_user"])) < TOL and normwise(iw.grad[::s], _t(gd["grad_item"])) < TOL
+    l64, gu64, gi64 = ref.loss_and_grads(u0.double(), i0.double(), train, neg, k)
+    assert abs(float(loss) - float(l64)) < TOL * abs(float(l64))
+    assert normwise(uw.grad, gu64) < TOL and normwise(iw.grad, gi64) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# fused training step (K1 + K3 + K2 + K6 in one C-ABI call)
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shape", ["tiny", "ml100k", "ml1m"])
+def test_fused_step_loss_grads_match_oracle(shape):
+    g, train, k, u0, i0 = _case(shape)
+    m = _model(g.num_users, g.num_items, k, u0, i0)
+    opt = tt.FusedAdam(m)
+    neg = _negs(train, g.num_users, g.num_items, 11)
+    loss = tt.train_step(m, opt, train.to(DEV), neg.to(DEV))
+    l64, gu64, gi64 = ref.loss_and_grads(u0.double(), i0.double(), train, neg, k)
+    assert abs(float(loss) - float(l64)) < TOL * abs(float(l64))
+    grad = opt.buffers.grad_e0.cpu()                                  # unclipped dL/de0
+    assert normwise(grad[: g.num_users], gu64) < TOL and normwise(grad[g.num_users:], gi64) < TOL
+    gn = float(torch.sqrt(gu64.pow(2).sum() + gi64.pow(2).sum()))
+    assert abs(float(opt.buffers.accum[2].sqrt()) - gn) < TOL * gn
+    assert torch.equal(opt.buffers.neg_count.cpu().long(), torch.bincount(neg, minlength=g.num_items))
+    assert int(opt.step_count) == 1
+
+
+@pytest.mark.parametrize("name", ["tiny_step.npz", "ml100k_step.npz"])
+def test_train_epoch_matches_reference_golden(golden, name):
+    """The reference's own train() over two batches (fixture) vs train() on the fused path."""
+    gd = golden(name)
+    g, train, k, u0, i0 = _case(str(gd["shape"]))
+    s = int(gd["row_stride"])
+    m = _model(g.num_users, g.num_items, k, u0, i0)
+    opt = tt.FusedAdam(m)
+    batches = [train[:, 0::2].contiguous().to(DEV), train[:, 1::2].contiguous().to(DEV)]
+    negs = [_t(gd["neg_b0"]).long().to(DEV), _t(gd["neg_b1"]).long().to(DEV)]
+    losses = [float(tt.train_step(m, opt, b, n)) for b, n in zip(batches, negs)]
+    w = [b.shape[1] for b in batches]
+    epoch = (losses[0] * w[0] + losses[1] * w[1]) / sum(w)
+    assert abs(epoch - float(gd["epoch_loss"])) < TOL * abs(float(gd["epoch_loss"]))
+    assert max_abs(m.user_embedding.weight.detach()[::s], _t(gd["user_w_after"])) < 2 * ADAM_STEP_ATOL
+    assert max_abs(m.item_embedding.weight.detach()[::s], _t(gd["item_w_after"])) < 2 * ADAM_STEP_ATOL
+    # evaluate(): loss over the val edges
+    val = g.edges("val").to(DEV)
+    vl = float(tt.eval_loss(m, val, _t(gd["val_neg"]).long().to(DEV)))
+    assert abs(vl - float(gd["val_loss"])) < 1e-4 * abs(float(gd["val_loss"]))
+    # sampled recall with the fixture's np.random draws
+    u, p, _ = get_triplets_indices(val, g.num_users, g.num_items, DEV)
+    uw, iw = m.user_embedding.weight.detach(), m.item_embedding.weight.detach()
+    vn = _t(gd["val_neg"]).long().to(DEV)
+    rec = tt.compute_recall_at_k((uw[u], iw[p], iw[vn]), k=100, sampled=list(gd["recall_draws"]))
+    assert abs(rec - float(gd["val_recall"])) < 2e-2 * float(gd["val_recall"])
+
+
+def test_multi_step_trajectory_vs_oracle():
+    g, train, k, u0, i0 = _case("tiny")
+    m = _model(g.num_users, g.num_items, k, u0, i0)
+    opt = tt.FusedAdam(m)
+    st = ref.TrainState(u0, i0, k)
+    ei = train.to(DEV)
+    for step in range(5):
+        neg = _negs(train, g.num_users, g.num_items, 100 + step)
+        l_gpu = float(tt.train_step(m, opt, ei, neg.to(DEV)))
+        l_cpu = st.step(train, neg)
+        assert abs(l_gpu - l_cpu) < 1e-4 * abs(l_cpu), (step, l_gpu, l_cpu)
+    assert max_abs(m.user_embedding.weight.detach(), st.user_w.detach()) < 5 * ADAM_STEP_ATOL
+    assert max_abs(m.item_embedding.weight.detach(), st.item_w.detach()) < 5 * ADAM_STEP_ATOL
+
+
+def test_clip_adam_kernel_against_torch_adam_on_identical_gradients():
+    nu, ni = 300, 200
+    gen = torch.Generator().manual_seed(0)
+    u0, i0 = torch.randn(nu, 64, generator=gen) * 0.01, torch.randn(ni, 64, generator=gen) * 0.01
+    m = _model(nu, ni, 1, u0, i0)
+    opt = tt.FusedAdam(m)
+    pu, pi = torch.nn.Parameter(u0.clone()), torch.nn.Parameter(i0.clone())
+    topt = torch.optim.Adam([pu, pi], lr=1e-3)
+    L = _lib.lib()
+    for step in range(4):
+        scale = [3.0, 0.02, 1.0, 0.5][step]                      # norm > 1 (clipped) and < 1 (not)
+        gfull = torch.randn(nu + ni, 64, generator=gen) * scale / 100
+        pu.grad, pi.grad = gfull[:nu].clone(), gfull[nu:].clone()
+        torch.nn.utils.clip_grad_norm_([pu, pi], max_norm=1)
+        topt.step()
+        gd = gfull.to(DEV)
+        _lib.check(L.lgcn_step_begin(opt.c, opt.buffers.accum.data_ptr(), _lib.stream_ptr(DEV)))
+        opt.buffers.accum[2] = gd.double().pow(2).sum()
+        _lib.check(L.lgcn_clip_adam(opt.c, m.user_embedding.weight.data_ptr(), m.item_embedding.weight.data_ptr(),
+                                    nu, ni, gd.data_ptr(), opt.buffers.accum.data_ptr(), 1, 5e-3, None,
+                                    _lib.stream_ptr(DEV)))
+        assert max_abs(m.user_embedding.weight.detach(), pu.detach()) < 2e-8 * (step + 1)
+        assert max_abs(m.item_embedding.weight.detach(), pi.detach()) < 2e-8 * (step + 1)
+    assert normwise(opt.exp_avg[:nu], topt.state[pu]["exp_avg"]) < 1e-6
+    assert normwise(opt.exp_avg_sq[nu:], topt.state[pi]["exp_avg_sq"]) < 1e-6
+
+
+def test_generic_optimizer_path_of_train():
+    """train() with a stock torch.optim.Adam (the reference's exact call sequence) vs the oracle."""
+    from lgcn_b200.data.dataset_handler import Data
+    g, train, k, u0, i0 = _case("tiny")
+    m = _model(g.num_users, g.num_items, k, u0, i0)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    batches = [Data(edge_index=train[:, 0::2].contiguous()), Data(edge_index=train[:, 1::2].contiguous())]
+    torch.manual_seed(9)
+    loss = tt.train(m, opt, batches, DEV)
+    assert np.isfinite(loss) and -1.0 < loss < 0.0
+    assert float((m.user_embedding.weight.detach().cpu() - u0).abs().max()) > 1e-4    # it stepped
+
+
+def test_no_fallback_on_cpu_tensors():
+    g, train, k, u0, i0 = _case("tiny")
+    m = LightGCN(g.num_users, g.num_items, num_layers=k)          # left on the CPU
+    with pytest.raises(_lib.LgcnError):
+        m(train)
+    with pytest.raises(_lib.LgcnError):
+        tt.bpr_loss(*[torch.zeros(4, 64)] * 6)
