@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- LightGCN hot-path benchmark (contract in the task statement / DESIGN.md sec. Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3]
+
+N = 1  workload C2 (BASELINE.json configs[1]): Cluster-GCN training on the synthetic ML-25M-shaped
+       graph (162,541 users x 59,047 movies, 25.0 M directed edges, 90 % train, 100 METIS parts,
+       K = 3, dim 64).  One STEP = one training epoch = 100 cluster-batch iterations of
+       utils/train_test.py:86-101 (forward, BPR loss, backward, clip, Adam).
+N > 1  workload C3: full-graph training step on the same graph, node-range sharded (see
+       lgcn_b200/sharded.py); launched under torchrun, one rank per GPU.
+metric  lightgcn_train_edges_per_s = directed batch-graph edges consumed per second by full training
+        steps (whole job); ms_per_step is the epoch (N=1) / full-graph step (N>1) time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import lgcn_b200  # noqa: E402,F401
+from lgcn_b200.data import synthetic  # noqa: E402
+
+METRIC, UNIT = "lightgcn_train_edges_per_s", "edges/s"
+NUM_PARTS = 100
+
+
+# --------------------------------------------------------------------------------------------
+# workload construction (untimed)
+# --------------------------------------------------------------------------------------------
+
+def load_partition(train: torch.Tensor, num_nodes: int, shape: str) -> torch.Tensor:
+    """METIS vector for the train graph: the committed fixture if it was computed on exactly these
+    edges (checksum), otherwise METIS is run here (~75 s at ML-25M)."""
+    fx = os.path.join(REPO, "tests", "golden", "ml25m_seed0_metis100.npz")
+    if shape == "ml25m" and os.path.exists(fx):
+        z = np.load(fx)
+        if int(z["train_checksum"]) == int((train[0] * 31 + train[1]).sum()) and int(z["num_parts"]) == NUM_PARTS:
+            return torch.from_numpy(z["cluster"].astype(np.int64))
+    from lgcn_b200.data.dataset_handler import metis_partition
+    return metis_partition(train, num_nodes, NUM_PARTS)
+
+
+def cluster_batches_cpu(train: torch.Tensor, cluster: torch.Tensor, num_nodes: int):
+    """Host-side list of the 100 cluster batches (global ids) for the CPU arms; same result as K4
+    (tests/test_gpu_cluster_score.py) -- train is (row, col)-sorted so a stable selection suffices."""
+    cr, cc = cluster[train[0]], cluster[train[1]]
+    keep = cr == cc
+    e, part = train[:, keep], cr[keep]
+    order = torch.sort(part, stable=True)[1]
+    e, part = e[:, order], part[order]
+    cnt = torch.bincount(part, minlength=NUM_PARTS)
+    off = torch.zeros(NUM_PARTS + 1, dtype=torch.long)
+    off[1:] = torch.cumsum(cnt, 0)
+    return [e[:, off[p]:off[p + 1]].contiguous() for p in range(NUM_PARTS)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port timed on the host cores (also `--impl reference`)
+# --------------------------------------------------------------------------------------------
+
+def cpu_sample_batches(batches):
+    """Three cluster batches at the 25/50/75-th size percentile: the per-batch CPU cost is dominated
+    by full-table (N x 64) work, so the epoch estimate is 100 x their mean time."""
+    sizes = np.array([b.shape[1] for b in batches])
+    order = np.argsort(sizes)
+    return [int(order[int(q * (len(order) - 1))]) for q in (0.25, 0.5, 0.75)]
+
+
+def run_cpu_arm(g, batches, k, steps, warmup):
+    from oracle import reference_path as ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
+    st = ref.TrainState(u0, i0, k)
+    pick = cpu_sample_batches(batches)
+    gen = torch.Generator().manual_seed(0)
+    total_edges = int(sum(b.shape[1] for b in batches))
+
+    def one_step():
+        t0 = time.perf_counter()
+        for p in pick:
+            ei = batches[p]
+            neg = torch.randint(0, g.num_items, (int((ei[0] < g.num_users).sum()),), generator=gen)
+            st.step(ei, neg)
+        return time.perf_counter() - t0
+
+    for _ in range(warmup):
+        one_step()
+    times = [one_step() for _ in range(steps)]
+    per_batch = float(np.mean(times)) / len(pick)
+    epoch_s = per_batch * len(batches)
+    sample = (f"{len(pick)} of {len(batches)} cluster batches per step (25/50/75th size percentile: "
+              f"{[int(batches[p].shape[1]) for p in pick]} edges), epoch time = {len(batches)} x mean batch time")
+    return {"value": total_edges / epoch_s, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": sample, "epoch_ms_estimate": epoch_s * 1e3, "ms_per_batch": per_batch * 1e3}
+
+
+# --------------------------------------------------------------------------------------------
+# ours, N = 1 (C2)
+# --------------------------------------------------------------------------------------------
+
+def run_c2(args):
+    from lgcn_b200 import _lib
+    from lgcn_b200.data.dataset_handler import ClusterData, ClusterLoader, Data
+    from lgcn_b200.models.light_gcn import LightGCN
+    from lgcn_b200.utils import train_test as tt
+
+    shape = {"c2": "ml25m", "c1": "ml100k"}[args.workload]
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    g = synthetic.make_graph(shape, seed=0)
+    k = synthetic.SHAPES[shape][3]
+    train = g.edges("train")
+    n = g.num_nodes
+    cluster = load_partition(train, n, shape)
+    t0 = time.perf_counter()
+    cd = ClusterData(Data(edge_index=train.to(dev), num_nodes=n), NUM_PARTS, cluster=cluster)
+    torch.cuda.synchronize()
+    extract_ms = (time.perf_counter() - t0) * 1e3
+    parts = [d for d in cd.parts]
+    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
+    model = LightGCN(g.num_users, g.num_items, num_layers=k).to(dev)
+    with torch.no_grad():
+        model.user_embedding.weight.copy_(u0)
+        model.item_embedding.weight.copy_(i0)
+    opt = tt.FusedAdam(model)
+    loader = ClusterLoader(parts, shuffle=True)
+    t0 = time.perf_counter()
+    graphs = [model.graph(d.edge_index) for d in parts]          # K0 once per batch tensor (cached)
+    torch.cuda.synchronize()
+    build_ms = (time.perf_counter() - t0) * 1e3
+    live = [d for d, gr in zip(parts, graphs) if gr.num_triplets > 0]
+    edges_per_epoch = int(sum(d.edge_index.shape[1] for d in live))
+    torch.manual_seed(0)
+
+    def epoch():
+        return tt.train(model, opt, loader, dev)
+
+    for _ in range(args.warmup):
+        epoch()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    losses = [epoch() for _ in range(args.steps)]
+    ev1.record()
+    torch.cuda.synchronize()
+    total_ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    ms_per_step = total_ms / args.steps
+    value = edges_per_epoch / (ms_per_step * 1e-3)
+
+    # ---- e2e: the same epoch through train() with HOST batches (pinned), H2D every step ----------
+    host_parts = [Data(edge_index=d.edge_index.cpu().pin_memory(), num_nodes=n) for d in live]
+
+    class HostLoader:
+        def __iter__(self):
+            for hp in host_parts:                                  # fresh device copy every time
+                yield Data(edge_index=hp.edge_index.to(dev, non_blocking=True), num_nodes=n)
+
+    model._graphs.capacity = 4                                     # per-step uploads must not pile up
+    for _ in range(1):
+        tt.train(model, opt, HostLoader(), dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(1, min(args.steps, 3))
+    e0.record()
+    for _ in range(e2e_steps):
+        tt.train(model, opt, HostLoader(), dev)                    # returns after the loss D2H
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    model._graphs.capacity = 512
+    h2d = int(sum(hp.edge_index.numel() * 8 for hp in host_parts))
+    e2e = {"value": edges_per_epoch / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * len(host_parts),
+           "note": "batches uploaded from pinned host memory every step, CSR rebuilt for each upload"}
+
+    # ---- per-stage device times over one epoch (events on the launch stream) ---------------------
+    stage_ms = stage_breakdown(model, opt, live, graphs_of(model, live), k, dev)
+    peak, peak_src = measured_peak_gbs()
+    adam_bytes = 7 * n * 256                                       # p,m,v,grad read + p,m,v written
+    adam_ms = stage_ms["clip_adam"] / len(live)
+    roofline = {"kernel": "clip_adam_kernel", "bound": "hbm", "achieved": adam_bytes / (adam_ms * 1e-3) / 1e9,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
+                "algorithmic_bytes_per_launch": adam_bytes, "avg_launch_ms": adam_ms}
+    roofline["frac"] = roofline["achieved"] / peak
+    spmm = full_graph_propagation(model, train.to(dev), k, dev, peak)
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"C2 Cluster-GCN training epoch, {shape} shape: U={g.num_users} I={g.num_items} "
+                                  f"E_train={train.shape[1]} directed, {NUM_PARTS} METIS parts "
+                                  f"({len(live)} non-empty, {edges_per_epoch} intra-cluster edges), K={k}, dim=64, "
+                                  "fwd+BPR+bwd+clip+Adam per batch, step = 1 epoch",
+                      "l2": "per-step working set (weights, Adam state, grads, activations ~ 8 x 56.7 MB) exceeds the "
+                            "126 MB L2; no explicit flush",
+                      "parallelism": "1 GPU"},
+           "clocks": clk, "e2e": e2e, "gpu_launches": int(args.steps * len(live) * launches_per_step(k)),
+           "roofline": roofline, "stage_ms_per_epoch": stage_ms, "spmm_full_graph": spmm,
+           "setup_ms": {"cluster_extract": extract_ms, "graph_build_100_batches": build_ms},
+           "final_epoch_loss": losses[-1]}
+    if not args.no_cpu:
+        out["cpu_baseline"] = run_cpu_arm(g, cluster_batches_cpu(train, cluster, n), k, 2, 1)
+    return out
+
+
+def launches_per_step(k: int) -> int:
+    # step_begin + inactive-row fwd + K fwd layers + BPR pass A + pass B + inactive-row bwd + K bwd + clip_adam
+    return 1 + 1 + k + 2 + 1 + k + 1
+
+
+def graphs_of(model, parts):
+    return [model.graph(d.edge_index) for d in parts]
+
+
+def stage_breakdown(model, opt, parts, graphs, k, dev):
+    """One epoch through the fine-grained C-ABI calls with an event pair around every stage."""
+    from ctypes import byref
+    from lgcn_b200 import _lib
+    L = _lib.lib()
+    s = _lib.stream_ptr(dev)
+    b = opt.buffers
+    uw, iw = model.user_embedding.weight, model.item_embedding.weight
+    names = ["step_begin", "propagate_fwd", "bpr_fwd_bwd", "propagate_bwd", "clip_adam"]
+    evs = {nm: [] for nm in names}
+    loss = torch.empty(1, device=dev)
+    for d, g in zip(parts, graphs):
+        neg = torch.randint(0, model.num_items, (g.num_triplets,), device=dev)
+        b.ensure_triplets(g.num_triplets)
+        reg = 2.0 * 5e-3 / (64.0 * g.num_triplets)
+        calls = [
+            lambda: L.lgcn_step_begin(byref(opt.c), b.accum.data_ptr(), s),
+            lambda: L.lgcn_propagate_fwd(g.ref, uw.data_ptr(), iw.data_ptr(), k, b.final_emb.data_ptr(),
+                                         b.rnorm.data_ptr(), b.work.data_ptr(), b.work.numel() * 4, s),
+            lambda: L.lgcn_bpr_fwd_bwd(g.ref, b.final_emb.data_ptr(), b.rnorm.data_ptr(), neg.data_ptr(),
+                                       b.grad_final.data_ptr(), b.neg_count.data_ptr(), b.trip_scratch.data_ptr(),
+                                       b.accum.data_ptr(), s),
+            lambda: L.lgcn_propagate_bwd(g.ref, b.grad_final.data_ptr(), k, uw.data_ptr(), iw.data_ptr(),
+                                         b.neg_count.data_ptr(), reg, b.grad_e0.data_ptr(), b.accum.data_ptr(),
+                                         b.work.data_ptr(), b.work.numel() * 4, s),
+            lambda: L.lgcn_clip_adam(byref(opt.c), uw.data_ptr(), iw.data_ptr(), model.num_users, model.num_items,
+                                     b.grad_e0.data_ptr(), b.accum.data_ptr(), g.num_triplets, 5e-3, loss.data_ptr(), s),
+        ]
+        for nm, fn in zip(names, calls):
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(fn())
+            z.record()
+            evs[nm].append((a, z))
+    torch.cuda.synchronize()
+    return {nm: float(sum(a.elapsed_time(z) for a, z in v)) for nm, v in evs.items()}
+
+
+def full_graph_propagation(model, train_dev, k, dev, peak):
+    """The SpMM figures of the metric: K-layer fused propagation over the whole train graph."""
+    from lgcn_b200 import _lib
+    L = _lib.lib()
+    g = model.graph(train_dev)
+    n, e = g.num_nodes, g.num_edges
+    final = torch.empty(n, 64, device=dev)
+    work = torch.empty(max(k - 1, 1) * n * 64, device=dev)
+    uw, iw = model.user_embedding.weight, model.item_embedding.weight
+
+    def run():
+        _lib.check(L.lgcn_propagate_fwd(g.ref, uw.data_ptr(), iw.data_ptr(), k, final.data_ptr(), None,
+                                        work.data_ptr(), work.numel() * 4, _lib.stream_ptr(dev)))
+    for _ in range(3):
+        run()
+    ts = []
+    for _ in range(10):
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); run(); z.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(z))
+    ms = float(np.median(ts))
+    b_layer = 2 * n * 256 + 8 * e + 4 * (n + 1)                    # SURVEY.md sec.8(d) contract figure
+    gather = e * 264 + n * 256 + 4 * (n + 1)
+    model._graphs.clear()
+    return {"edges": e, "layers": k, "ms": ms, "edges_per_s": e * k / (ms * 1e-3),
+            "algorithmic_gbs": k * b_layer / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": k * b_layer / (ms * 1e-3) / 1e9 / peak,
+            "gather_model_gbs": k * gather / (ms * 1e-3) / 1e9}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm
+# --------------------------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    shape = {"c2": "ml25m", "c1": "ml100k", "c3": "ml25m"}[args.workload]
+    g = synthetic.make_graph(shape, seed=0)
+    k = synthetic.SHAPES[shape][3]
+    train = g.edges("train")
+    cluster = load_partition(train, g.num_nodes, shape)
+    batches = [b for b in cluster_batches_cpu(train, cluster, g.num_nodes) if int((b[0] < g.num_users).sum()) > 0]
+    cpu = run_cpu_arm(g, batches, k, args.steps, args.warmup)
+    return {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["epoch_ms_estimate"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C2 Cluster-GCN training epoch, {shape} shape, {NUM_PARTS} METIS parts, K={k}, dim=64; "
+                                   "reference CPU path = oracle port of the PyG gather/scatter op sequence "
+                                   "(PyG/torch_sparse not installable offline), torch CPU, all host threads"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "c2" if args.gpus == 1 else "c3"
+    if args.impl == "reference":
+        if args.workload == "c3":
+            args.workload = "c2"
+        out = run_reference(args)
+        if out is not None:
+            print(json.dumps(out))
+        return
+    if args.gpus == 1 and args.workload in ("c1", "c2"):
+        out = run_c2(args)
+    else:
+        from lgcn_b200 import sharded
+        out = sharded.bench_c3(args)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -90,6 +90,7 @@ class FusedAdam:
         self.step_count = torch.zeros(1, dtype=torch.int64, device=w.device)
         self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
         self.buffers = StepBuffers(n, model.num_items, model.num_layers, w.device)
+        self.losses = torch.zeros(1024, dtype=torch.float32, device=w.device)   # per-batch losses of an epoch
         self.c = CAdam()
         self._fill()
 
@@ -100,6 +101,13 @@ class FusedAdam:
 
     def zero_grad(self):
         pass
+
+    def loss_slot(self, i: int) -> torch.Tensor:
+        if i >= self.losses.numel():
+            grown = torch.zeros(2 * self.losses.numel(), dtype=torch.float32, device=self.losses.device)
+            grown[: self.losses.numel()] = self.losses
+            self.losses = grown
+        return self.losses[i:i + 1]
 
     def state_dict(self):
         return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,
@@ -140,15 +148,18 @@ def train(model: torch.nn.Module, optimizer, train_loader, device: torch.device)
     """One epoch (utils/train_test.py:66-103): edge-count-weighted mean of the batch losses."""
     model.train()
     if isinstance(optimizer, FusedAdam):
-        batches = [b.to(device) for b in train_loader]
-        batches = [b for b in batches if b.edge_index.shape[1] > 0 and model.graph(b.edge_index).num_triplets > 0]
-        if not batches:
+        weights = []
+        for batch in train_loader:
+            batch = batch.to(device)
+            if batch.edge_index.shape[1] == 0 or model.graph(batch.edge_index).num_triplets == 0:
+                continue                      # the reference would produce NaN here (App. B #13)
+            train_step(model, optimizer, batch.edge_index, loss_out=optimizer.loss_slot(len(weights)))
+            weights.append(batch.edge_index.shape[1])
+        if not weights:
             return float("nan")
-        losses = torch.empty(len(batches), dtype=torch.float32, device=device)
-        for i, batch in enumerate(batches):
-            train_step(model, optimizer, batch.edge_index, loss_out=losses[i:i + 1])
-        w = torch.tensor([b.edge_index.shape[1] for b in batches], dtype=torch.float64)
-        return float((losses.double().cpu() * w).sum() / w.sum())        # the epoch's only sync
+        w = torch.tensor(weights, dtype=torch.float64)
+        losses = optimizer.losses[: len(weights)].double().cpu()          # the epoch's only sync
+        return float((losses * w).sum() / w.sum())
 
     total_loss, total_w = 0.0, 0
     for batch in train_loader:
