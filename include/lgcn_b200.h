@@ -157,8 +157,7 @@ int lgcn_bpr_rows(const float *uf, const float *u0, const float *pf, const float
 /* ---- K6: clip_grad_norm_(max_norm) + Adam ------------------------------------------------ */
 
 typedef struct lgcn_adam {
-    float lr, beta1, beta2, eps, max_norm;
-    int32_t pad;
+    double lr, beta1, beta2, eps, max_norm;   /* doubles: torch derives 1-beta, lr/(1-beta^t) in double */
     int64_t *step;          /* device int64: incremented by lgcn_step_begin             */
     float *m, *v;           /* [N,64] exp_avg / exp_avg_sq                              */
 } lgcn_adam;

@@ -58,8 +58,8 @@ class CGraphSizes(Structure):
 
 
 class CAdam(Structure):
-    _fields_ = [("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
-                ("max_norm", c_float), ("pad", c_int32), ("step", c_void_p), ("m", c_void_p), ("v", c_void_p)]
+    _fields_ = [("lr", c_double), ("beta1", c_double), ("beta2", c_double), ("eps", c_double),
+                ("max_norm", c_double), ("step", c_void_p), ("m", c_void_p), ("v", c_void_p)]
 
 
 class CStepBuffers(Structure):

@@ -20,18 +20,20 @@ __global__ void step_begin_kernel(int64_t *step, double *accum) {
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float4 *__restrict__ user_w, float4 *__restrict__ item_w, size_t user_vec, size_t total_vec,
                  const float4 *__restrict__ grad, float4 *__restrict__ m, float4 *__restrict__ v,
-                 const double *__restrict__ accum, const int64_t *__restrict__ step, float lr, float beta1,
-                 float beta2, float eps, float max_norm, int64_t P, float coeff, float *loss_out) {
+                 const double *__restrict__ accum, const int64_t *__restrict__ step, double lr_d, double beta1_d,
+                 double beta2_d, double eps_d, double max_norm_d, int64_t P, float coeff, float *loss_out) {
     // per-thread scalars (same value in every thread; cheap next to the streaming loop)
+    // scalars follow torch's _single_tensor_adam: Python-double arithmetic, then one cast to fp32
     const double t = (double)step[0];
-    const double bc1 = 1.0 - pow((double)beta1, t);
-    const double bc2 = 1.0 - pow((double)beta2, t);
-    const float step_size = (float)((double)lr / bc1);
+    const double bc1 = 1.0 - pow(beta1_d, t);
+    const double bc2 = 1.0 - pow(beta2_d, t);
+    const float step_size = (float)(lr_d / bc1);
+    const float beta2 = (float)beta2_d, eps = (float)eps_d, max_norm = (float)max_norm_d;
     const float bc2_sqrt = (float)sqrt(bc2);
     const float total_norm = (float)sqrt(accum[2]);
     float clip = max_norm > 0.f ? max_norm / (total_norm + 1e-6f) : 1.0f;   // max_norm <= 0: no clipping
     clip = fminf(clip, 1.0f);
-    const float w1 = 1.0f - beta1, w2 = 1.0f - beta2;
+    const float w1 = (float)(1.0 - beta1_d), w2 = (float)(1.0 - beta2_d);
     if (loss_out && blockIdx.x == 0 && threadIdx.x == 0) {
         const double p = (double)P;
         loss_out[0] = (float)(-accum[0] / (10.0 * p) + (double)coeff * accum[1] / (64.0 * p));

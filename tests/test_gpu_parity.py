@@ -3,6 +3,8 @@ same seeded inputs, against the golden fixtures produced by the unmodified refer
 size-independent properties.  Bars: integer structures bit-exact; fp32 tensors normwise 1e-5
 (max|d| <= 1e-5 max|ref|) against the fp64 oracle; post-optimiser weights per
 conftest.ADAM_STEP_ATOL."""
+from ctypes import byref
+
 import numpy as np
 import pytest
 import torch
@@ -282,9 +284,9 @@ def test_clip_adam_kernel_against_torch_adam_on_identical_gradients():
         torch.nn.utils.clip_grad_norm_([pu, pi], max_norm=1)
         topt.step()
         gd = gfull.to(DEV)
-        _lib.check(L.lgcn_step_begin(opt.c, opt.buffers.accum.data_ptr(), _lib.stream_ptr(DEV)))
+        _lib.check(L.lgcn_step_begin(byref(opt.c), opt.buffers.accum.data_ptr(), _lib.stream_ptr(DEV)))
         opt.buffers.accum[2] = gd.double().pow(2).sum()
-        _lib.check(L.lgcn_clip_adam(opt.c, m.user_embedding.weight.data_ptr(), m.item_embedding.weight.data_ptr(),
+        _lib.check(L.lgcn_clip_adam(byref(opt.c), m.user_embedding.weight.data_ptr(), m.item_embedding.weight.data_ptr(),
                                     nu, ni, gd.data_ptr(), opt.buffers.accum.data_ptr(), 1, 5e-3, None,
                                     _lib.stream_ptr(DEV)))
         assert max_abs(m.user_embedding.weight.detach(), pu.detach()) < 2e-8 * (step + 1)
