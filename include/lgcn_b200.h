@@ -172,6 +172,34 @@ int lgcn_clip_adam(const lgcn_adam *opt, float *user_w, float *item_w, int64_t n
                    int64_t num_items, const float *grad, const double *accum,
                    int64_t num_triplets, float bpr_coeff, float *loss_out, void *stream);
 
+/* ---- sharded (owner-computes by node range) building blocks -------------------------------
+ * Every rank holds the FULL lgcn_graph and executes only the warp tasks whose rows it owns
+ * ([task_begin,task_end) of the row-sorted task list covering rows [row_begin,row_end)); the
+ * caller exchanges the produced row slabs between layers (NCCL all-gather / all-reduce, see
+ * lgcn_b200/sharded.py).  Layer 1 here reads the PRE-SCALED table y0 = dis (.) e0. */
+int lgcn_prescale(const lgcn_graph *g, const float *user_w, const float *item_w, int64_t row_begin,
+                  int64_t row_end, float *y0, void *stream);
+int lgcn_fwd_layer(const lgcn_graph *g, const float *user_w, const float *item_w, int k, int num_layers,
+                   const float *yin, float *yout, const float *y1, const float *y2, const float *y3,
+                   float *final_out, float *rnorm, int task_begin, int task_end, int64_t row_begin,
+                   int64_t row_end, void *stream);
+int lgcn_bwd_layer(const lgcn_graph *g, const float *grad_final, int j, int num_layers, const float *zin,
+                   float *zout, const float *user_w, const float *item_w, const int32_t *neg_count,
+                   float reg_coef, float *grad_e0, double *accum, int task_begin, int task_end,
+                   int64_t row_begin, int64_t row_end, void *stream);
+/* lgcn_bpr_fwd_bwd restricted to the triplets of users [user_row_begin,user_row_end) (out-task range
+ * [user_task_begin,user_task_end)); grad_final / neg_count are zeroed first so that the per-rank
+ * results sum to the unsharded ones. */
+int lgcn_bpr_fwd_bwd_range(const lgcn_graph *g, const float *final_emb, const float *rnorm,
+                           const int64_t *neg, float *grad_final, int32_t *neg_count,
+                           float *trip_scratch, double *accum, int user_task_begin, int user_task_end,
+                           int64_t user_row_begin, int64_t user_row_end, void *stream);
+/* lgcn_clip_adam over rows [row_begin,row_end) only (accum must already hold the GLOBAL sums). */
+int lgcn_clip_adam_rows(const lgcn_adam *opt, float *user_w, float *item_w, int64_t num_users,
+                        int64_t num_items, const float *grad, const double *accum,
+                        int64_t num_triplets, float bpr_coeff, float *loss_out, int64_t row_begin,
+                        int64_t row_end, void *stream);
+
 /* ---- fused training step ------------------------------------------------------------------ */
 
 typedef struct lgcn_step_buffers {

@@ -26,7 +26,8 @@ EXPORTS = [
     "lgcn_propagate_fwd", "lgcn_propagate_bwd", "lgcn_bpr_fwd_bwd", "lgcn_step_begin",
     "lgcn_clip_adam", "lgcn_train_step", "lgcn_eval_loss", "lgcn_partition_metis",
     "lgcn_cluster_extract_workspace_bytes", "lgcn_cluster_extract", "lgcn_score_topk",
-    "lgcn_spmm", "lgcn_bpr_rows",
+    "lgcn_spmm", "lgcn_bpr_rows", "lgcn_prescale", "lgcn_fwd_layer", "lgcn_bwd_layer",
+    "lgcn_bpr_fwd_bwd_range", "lgcn_clip_adam_rows",
 ]
 
 
@@ -106,6 +107,14 @@ def lib():
                                   c_void_p, c_void_p, c_void_p]
     L.lgcn_spmm.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int, c_void_p]
     L.lgcn_bpr_rows.argtypes = [c_void_p] * 6 + [c_int64, c_float, c_void_p, c_void_p, c_void_p] + [c_void_p] * 6 + [c_void_p]
+    L.lgcn_prescale.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]
+    L.lgcn_fwd_layer.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 7 + \
+        [c_int, c_int, c_int64, c_int64, c_void_p]
+    L.lgcn_bwd_layer.argtypes = [POINTER(CGraph), c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p]
+    L.lgcn_bpr_fwd_bwd_range.argtypes = [POINTER(CGraph)] + [c_void_p] * 7 + [c_int, c_int, c_int64, c_int64, c_void_p]
+    L.lgcn_clip_adam_rows.argtypes = [POINTER(CAdam), c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                      c_float, c_void_p, c_int64, c_int64, c_void_p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("lgcn_last_error", "lgcn_cluster_extract_workspace_bytes"):

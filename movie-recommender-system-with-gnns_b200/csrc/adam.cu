@@ -18,7 +18,8 @@ __global__ void step_begin_kernel(int64_t *step, double *accum) {
 }
 
 __global__ void __launch_bounds__(256)
-clip_adam_kernel(float4 *__restrict__ user_w, float4 *__restrict__ item_w, size_t user_vec, size_t total_vec,
+clip_adam_kernel(float4 *__restrict__ user_w, float4 *__restrict__ item_w, size_t user_vec, size_t vec_begin,
+                 size_t total_vec,
                  const float4 *__restrict__ grad, float4 *__restrict__ m, float4 *__restrict__ v,
                  const double *__restrict__ accum, const int64_t *__restrict__ step, double lr_d, double beta1_d,
                  double beta2_d, double eps_d, double max_norm_d, int64_t P, float coeff, float *loss_out) {
@@ -39,7 +40,7 @@ clip_adam_kernel(float4 *__restrict__ user_w, float4 *__restrict__ item_w, size_
         loss_out[0] = (float)(-accum[0] / (10.0 * p) + (double)coeff * accum[1] / (64.0 * p));
     }
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+    for (size_t i = vec_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += stride) {
         float4 *pp = i < user_vec ? user_w + i : item_w + (i - user_vec);
         const float4 g4 = __ldcs(grad + i);
         float4 p4 = *pp, m4 = m[i], v4 = v[i];
@@ -66,22 +67,37 @@ extern "C" int lgcn_step_begin(const lgcn_adam *opt, double *accum, void *stream
     return LGCN_OK;
 }
 
-extern "C" int lgcn_clip_adam(const lgcn_adam *opt, float *user_w, float *item_w, int64_t num_users,
-                              int64_t num_items, const float *grad, const double *accum,
-                              int64_t num_triplets, float bpr_coeff, float *loss_out, void *stream) {
+extern "C" int lgcn_clip_adam_rows(const lgcn_adam *opt, float *user_w, float *item_w, int64_t num_users,
+                                   int64_t num_items, const float *grad, const double *accum,
+                                   int64_t num_triplets, float bpr_coeff, float *loss_out, int64_t row_begin,
+                                   int64_t row_end, void *stream) {
     LGCN_REQUIRE(opt && user_w && item_w && grad && accum && opt->m && opt->v && opt->step, LGCN_E_INVALID,
                  "clip_adam: null argument");
-    const size_t user_vec = (size_t)num_users * lgcn::D4, total = (size_t)(num_users + num_items) * lgcn::D4;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t want = (int64_t)((total + 255) / 256);
+    LGCN_REQUIRE(row_begin >= 0 && row_end <= num_users + num_items && row_begin <= row_end, LGCN_E_INVALID,
+                 "clip_adam: bad row range");
+    const size_t user_vec = (size_t)num_users * lgcn::D4;
+    const size_t vb = (size_t)row_begin * lgcn::D4, ve = (size_t)row_end * lgcn::D4;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const int64_t want = (int64_t)((ve - vb + 255) / 256);
     const int grid = (int)(want < (int64_t)sms * 8 ? (want > 0 ? want : 1) : (int64_t)sms * 8);
     lgcn::clip_adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<float4 *>(user_w), reinterpret_cast<float4 *>(item_w), user_vec, total,
+        reinterpret_cast<float4 *>(user_w), reinterpret_cast<float4 *>(item_w), user_vec, vb, ve,
         reinterpret_cast<const float4 *>(grad), reinterpret_cast<float4 *>(opt->m),
         reinterpret_cast<float4 *>(opt->v), accum, opt->step, opt->lr, opt->beta1, opt->beta2, opt->eps,
         opt->max_norm, num_triplets, bpr_coeff, loss_out);
     LGCN_LAUNCH_CHECK();
     return LGCN_OK;
+}
+
+extern "C" int lgcn_clip_adam(const lgcn_adam *opt, float *user_w, float *item_w, int64_t num_users,
+                              int64_t num_items, const float *grad, const double *accum,
+                              int64_t num_triplets, float bpr_coeff, float *loss_out, void *stream) {
+    return lgcn_clip_adam_rows(opt, user_w, item_w, num_users, num_items, grad, accum, num_triplets, bpr_coeff,
+                               loss_out, 0, num_users + num_items, stream);
 }

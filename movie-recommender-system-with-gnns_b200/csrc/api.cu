@@ -19,7 +19,7 @@ int propagate_fwd_impl(const lgcn_graph *, const float *, const float *, int, fl
 int propagate_bwd_impl(const lgcn_graph *, const float *, int, const float *, const float *, const int32_t *, float,
                        float *, double *, float *, size_t, cudaStream_t);
 int bpr_impl(const lgcn_graph *, const float *, const float *, const int64_t *, float *, int32_t *, float *,
-             double *, bool, cudaStream_t);
+             double *, bool, int, int, int, int, cudaStream_t);
 int reg_value_impl(const lgcn_graph *, const float *, const float *, const int32_t *, double *, cudaStream_t);
 int loss_finalize_impl(const double *, int64_t, float, float *, cudaStream_t);
 
@@ -51,7 +51,7 @@ extern "C" int lgcn_train_step(const lgcn_graph *g, float *user_w, float *item_w
     if ((rc = propagate_fwd_impl(g, user_w, item_w, num_layers, buf->final_emb, buf->rnorm, buf->work,
                                  buf->work_bytes, st))) return rc;
     if ((rc = bpr_impl(g, buf->final_emb, buf->rnorm, neg, buf->grad_final, buf->neg_count, buf->trip_scratch,
-                       buf->accum, true, st))) return rc;
+                       buf->accum, true, 0, g->n_out_user_tasks, 0, g->num_users, st))) return rc;
     // regulariser gradient 2*coeff/(64 P) * cnt[r] * e0[r] is folded into the last backward layer
     const float reg_coef = 2.0f * bpr_coeff / (64.0f * (float)g->num_triplets);
     if ((rc = propagate_bwd_impl(g, buf->grad_final, num_layers, user_w, item_w, buf->neg_count, reg_coef,
@@ -73,8 +73,8 @@ extern "C" int lgcn_eval_loss(const lgcn_graph *g, const float *user_w, const fl
     if ((rc = lgcn_step_begin(nullptr, buf->accum, stream))) return rc;
     if ((rc = propagate_fwd_impl(g, user_w, item_w, num_layers, buf->final_emb, buf->rnorm, buf->work,
                                  buf->work_bytes, st))) return rc;
-    if ((rc = bpr_impl(g, buf->final_emb, buf->rnorm, neg, nullptr, buf->neg_count, nullptr, buf->accum, false,
-                       st))) return rc;
+    if ((rc = bpr_impl(g, buf->final_emb, buf->rnorm, neg, nullptr, buf->neg_count, nullptr, buf->accum, false, 0,
+                       g->n_out_user_tasks, 0, g->num_users, st))) return rc;
     if ((rc = reg_value_impl(g, user_w, item_w, buf->neg_count, buf->accum + 1, st))) return rc;
     return loss_finalize_impl(buf->accum, g->num_triplets, bpr_coeff, loss_out, st);
 }

@@ -145,6 +145,7 @@ struct BprItemOp {
     const float *F, *rnorm, *scratch;
     float invP;
     float *G;
+    int ub, ue;                 // only triplets of users in [ub,ue) are accumulated (sharded path)
 
     __device__ __forceinline__ void accumulate(int, int begin, int end, int lane, float4 &acc, float &sc,
                                                float &, float &) const {
@@ -155,8 +156,9 @@ struct BprItemOp {
             [&](int e) {
                 TripItemB it;
                 it.u = -1; it.s = 0.f; it.scp = 0.f; it.ru = 0.f; it.vu = f4zero();
-                if (e >= 0) {
-                    it.u = __ldg(in_nbr + e);
+                if (e >= 0) it.u = __ldg(in_nbr + e);
+                if (it.u < ub || it.u >= ue) it.u = -1;
+                if (it.u >= 0) {
                     const float2 sc2 = __ldg(reinterpret_cast<const float2 *>(scratch) + __ldg(in_trip + e));
                     it.ru = __ldg(rnorm + it.u);
                     it.s = sc2.x * it.ru;                 // s_t / ||u||
@@ -219,8 +221,11 @@ __global__ void loss_finalize_kernel(const double *accum, int64_t P, float coeff
     loss_out[0] = (float)(-accum[0] / (10.0 * p) + (double)coeff * accum[1] / (64.0 * p));
 }
 
+// Triplets of the users covered by out-tasks [utb,ute) / rows [urb,ure) only (everything: 0,
+// n_out_user_tasks, 0, num_users).  G and neg_count are zeroed first, so per-rank results can be summed.
 int bpr_impl(const lgcn_graph *g, const float *F, const float *rnorm, const int64_t *neg, float *G,
-             int32_t *neg_count, float *scratch, double *accum, bool grad, cudaStream_t st) {
+             int32_t *neg_count, float *scratch, double *accum, bool grad, int utb, int ute, int urb, int ure,
+             cudaStream_t st) {
     LGCN_REQUIRE(g && F && rnorm && neg && neg_count && accum, LGCN_E_INVALID, "bpr: null argument");
     LGCN_REQUIRE(!grad || (G && scratch), LGCN_E_INVALID, "bpr: gradient buffers missing");
     const int num_items = g->num_nodes - g->num_users;
@@ -234,14 +239,14 @@ int bpr_impl(const lgcn_graph *g, const float *F, const float *rnorm, const int6
         LGCN_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)g->num_nodes * D, st));
         BprUserOp<true> a{accum, nullptr, g->out_nbr, g->out_trip, neg, F, rnorm, g->num_users, invP, G,
                           neg_count, scratch};
-        LGCN_CUDA(launch_rowtasks(a, g->out_tasks, 0, g->n_out_user_tasks, g->partials, g->slot_counters, st));
-        BprItemOp b{nullptr, nullptr, g->in_nbr, g->in_trip, F, rnorm, scratch, invP, G};
+        LGCN_CUDA(launch_rowtasks(a, g->out_tasks, utb, ute, g->partials, g->slot_counters, st));
+        BprItemOp b{nullptr, nullptr, g->in_nbr, g->in_trip, F, rnorm, scratch, invP, G, urb, ure};
         LGCN_CUDA(launch_rowtasks(b, g->in_tasks, g->n_in_user_tasks, g->n_in_tasks, g->partials,
                                   g->slot_counters, st));
     } else {
         BprUserOp<false> a{accum, nullptr, g->out_nbr, g->out_trip, neg, F, rnorm, g->num_users, invP,
                            nullptr, neg_count, nullptr};
-        LGCN_CUDA(launch_rowtasks(a, g->out_tasks, 0, g->n_out_user_tasks, g->partials, g->slot_counters, st));
+        LGCN_CUDA(launch_rowtasks(a, g->out_tasks, utb, ute, g->partials, g->slot_counters, st));
     }
     return LGCN_OK;
 }
@@ -266,6 +271,17 @@ int loss_finalize_impl(const double *accum, int64_t P, float coeff, float *loss_
 extern "C" int lgcn_bpr_fwd_bwd(const lgcn_graph *g, const float *final_emb, const float *rnorm,
                                 const int64_t *neg, float *grad_final, int32_t *neg_count,
                                 float *trip_scratch, double *accum, void *stream) {
-    return lgcn::bpr_impl(g, final_emb, rnorm, neg, grad_final, neg_count, trip_scratch, accum, true,
-                          (cudaStream_t)stream);
+    LGCN_REQUIRE(g, LGCN_E_INVALID, "bpr: null graph");
+    return lgcn::bpr_impl(g, final_emb, rnorm, neg, grad_final, neg_count, trip_scratch, accum, true, 0,
+                          g->n_out_user_tasks, 0, g->num_users, (cudaStream_t)stream);
+}
+
+extern "C" int lgcn_bpr_fwd_bwd_range(const lgcn_graph *g, const float *final_emb, const float *rnorm,
+                                      const int64_t *neg, float *grad_final, int32_t *neg_count,
+                                      float *trip_scratch, double *accum, int user_task_begin, int user_task_end,
+                                      int64_t user_row_begin, int64_t user_row_end, void *stream) {
+    LGCN_REQUIRE(g && user_task_begin >= 0 && user_task_end <= g->n_out_user_tasks && user_task_begin <= user_task_end &&
+                 user_row_begin >= 0 && user_row_end <= g->num_users, LGCN_E_INVALID, "bpr_range: bad range");
+    return lgcn::bpr_impl(g, final_emb, rnorm, neg, grad_final, neg_count, trip_scratch, accum, true, user_task_begin,
+                          user_task_end, (int)user_row_begin, (int)user_row_end, (cudaStream_t)stream);
 }

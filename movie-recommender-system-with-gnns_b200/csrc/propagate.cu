@@ -129,10 +129,10 @@ struct FwdOp {
 
 // Rows without any incident edge: final = e0 / (K+1)^2 (every propagated layer is zero).
 __global__ void __launch_bounds__(CTA_THREADS)
-fwd_inactive_kernel(Table e0, const uint8_t *__restrict__ active, int n, float c0,
+fwd_inactive_kernel(Table e0, const uint8_t *__restrict__ active, int row0, int n, float c0,
                     float *__restrict__ final_out, float *__restrict__ rnorm) {
     const int lane = threadIdx.x & 31, l16 = lane & 15;
-    int row = (blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) * 2 + (lane >> 4);
+    int row = row0 + (blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) * 2 + (lane >> 4);
     const bool ok = row < n && !active[row];
     float4 f = f4zero();
     if (ok) {
@@ -198,11 +198,11 @@ struct BwdOp {
 
 // Rows without incident edges: grad = G/(K+1)^2 + reg (only sampled negatives reach them).
 __global__ void __launch_bounds__(CTA_THREADS)
-bwd_inactive_kernel(const float *__restrict__ G, const uint8_t *__restrict__ active, int n, float c0,
+bwd_inactive_kernel(const float *__restrict__ G, const uint8_t *__restrict__ active, int row0, int n, float c0,
                     Table e0, const int32_t *__restrict__ neg_count, float reg_coef, int num_users,
                     float *__restrict__ grad, double *extra0, double *extra1) {
     const int lane = threadIdx.x & 31, l16 = lane & 15, wid = threadIdx.x >> 5;
-    int row = (blockIdx.x * WARPS_PER_CTA + wid) * 2 + (lane >> 4);
+    int row = row0 + (blockIdx.x * WARPS_PER_CTA + wid) * 2 + (lane >> 4);
     const bool ok = row < n && !active[row];
     float4 g = f4zero();
     float reg = 0.f;
@@ -235,13 +235,74 @@ bwd_inactive_kernel(const float *__restrict__ G, const uint8_t *__restrict__ act
 // host drivers
 // ---------------------------------------------------------------------------------------
 
-template <bool kFirst, bool kLast>
-static cudaError_t launch_fwd(const lgcn_graph *g, const FwdOp<kFirst, kLast> &op, cudaStream_t st) {
-    return launch_rowtasks(op, g->in_tasks, 0, g->n_in_tasks, g->partials, g->slot_counters, st);
+// y0[r] = dis[r] * e0[r] for rows [row_begin,row_end): lets layer 1 run as a pure gather-sum when the
+// table is assembled from per-rank slabs (sharded path).
+__global__ void __launch_bounds__(CTA_THREADS)
+prescale_kernel(Table e0, const float *__restrict__ dis, int row0, int n, float *__restrict__ y0) {
+    const int lane = threadIdx.x & 31, l16 = lane & 15;
+    const int row = row0 + (blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) * 2 + (lane >> 4);
+    if (row < n)
+        reinterpret_cast<float4 *>(y0)[(size_t)row * D4 + l16] = f4scale(__ldg(dis + row), ldg4(e0.row4(row) + l16));
 }
-template <bool kFirst, bool kLast>
-static cudaError_t launch_bwd(const lgcn_graph *g, const BwdOp<kFirst, kLast> &op, cudaStream_t st) {
-    return launch_rowtasks(op, g->out_tasks, 0, g->n_out_tasks, g->partials, g->slot_counters, st);
+
+struct Range {              // tasks [tb,te) of the list and the node rows [rb,re) they cover
+    int tb, te, rb, re;
+};
+
+// One forward layer k of K over the tasks of `r`.  scaled_first: layer 1 reads e0 and applies dis[r]
+// per edge (single-GPU path); otherwise yin is the pre-scaled table y_{k-1} for every layer.
+int fwd_layer_impl(const lgcn_graph *g, const Table &e0, int k, int K, bool scaled_first, const float *yin,
+                   float *yout, const float *y1, const float *y2, const float *y3, float *final_out,
+                   float *rnorm, Range r, cudaStream_t st) {
+    const float c0 = 1.0f / (float)((K + 1) * (K + 1));
+    const bool first = k == 1 && scaled_first, last = k == K;
+    if (last && g->num_active < g->num_nodes && r.re > r.rb) {
+        fwd_inactive_kernel<<<cdiv(r.re - r.rb, 2 * WARPS_PER_CTA), CTA_THREADS, 0, st>>>(
+            e0, g->active, r.rb, r.re, c0, final_out, rnorm);
+        LGCN_LAUNCH_CHECK();
+    }
+    auto go = [&](auto op) { return launch_rowtasks(op, g->in_tasks, r.tb, r.te, g->partials, g->slot_counters, st); };
+    if (first && last)
+        LGCN_CUDA(go(FwdOp<true, true>{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, nullptr, nullptr,
+                                       {nullptr, nullptr, nullptr}, 0, c0, final_out, rnorm}));
+    else if (first)
+        LGCN_CUDA(go(FwdOp<true, false>{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, nullptr, yout,
+                                        {nullptr, nullptr, nullptr}, 0, c0, nullptr, nullptr}));
+    else if (!last)
+        LGCN_CUDA(go(FwdOp<false, false>{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, yin, yout,
+                                         {nullptr, nullptr, nullptr}, 0, c0, nullptr, nullptr}));
+    else
+        LGCN_CUDA(go(FwdOp<false, true>{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, yin, nullptr,
+                                        {y1, y2, y3}, K - 1, c0, final_out, rnorm}));
+    return LGCN_OK;
+}
+
+// One backward (Horner) layer j of K over the tasks of `r`; layer 1 gathers dis (.) G itself.
+int bwd_layer_impl(const lgcn_graph *g, const float *G, int j, int K, const float *zin, float *zout,
+                   const Table &e0, const int32_t *neg_count, float reg_coef, float *grad, double *accum,
+                   Range r, cudaStream_t st) {
+    const float c0 = 1.0f / (float)((K + 1) * (K + 1));
+    const bool first = j == 1, last = j == K;
+    double *ex0 = accum ? accum + 1 : nullptr, *ex1 = accum ? accum + 2 : nullptr;
+    if (last && g->num_active < g->num_nodes && r.re > r.rb) {
+        bwd_inactive_kernel<<<cdiv(r.re - r.rb, 2 * WARPS_PER_CTA), CTA_THREADS, 0, st>>>(
+            G, g->active, r.rb, r.re, c0, e0, neg_count, reg_coef, g->num_users, grad, ex0, ex1);
+        LGCN_LAUNCH_CHECK();
+    }
+    auto go = [&](auto op) { return launch_rowtasks(op, g->out_tasks, r.tb, r.te, g->partials, g->slot_counters, st); };
+    if (first && last)
+        LGCN_CUDA(go(BwdOp<true, true>{ex0, ex1, g->out_nbr, g->in_ptr, g->out_ptr, g->dis, G, zin, zout, c0, grad, e0,
+                                       neg_count, reg_coef, g->num_users}));
+    else if (first)
+        LGCN_CUDA(go(BwdOp<true, false>{nullptr, nullptr, g->out_nbr, g->in_ptr, g->out_ptr, g->dis, G, zin, zout, c0,
+                                        grad, e0, neg_count, reg_coef, g->num_users}));
+    else if (!last)
+        LGCN_CUDA(go(BwdOp<false, false>{nullptr, nullptr, g->out_nbr, g->in_ptr, g->out_ptr, g->dis, G, zin, zout, c0,
+                                         grad, e0, neg_count, reg_coef, g->num_users}));
+    else
+        LGCN_CUDA(go(BwdOp<false, true>{ex0, ex1, g->out_nbr, g->in_ptr, g->out_ptr, g->dis, G, zin, zout, c0, grad, e0,
+                                        neg_count, reg_coef, g->num_users}));
+    return LGCN_OK;
 }
 
 int propagate_fwd_impl(const lgcn_graph *g, const float *user_w, const float *item_w, int K,
@@ -253,33 +314,13 @@ int propagate_fwd_impl(const lgcn_graph *g, const float *user_w, const float *it
                  LGCN_E_WORKSPACE, "propagate_fwd: workspace %zu < %zu bytes", work_bytes,
                  (size_t)(K - 1) * n * D * sizeof(float));
     const Table e0{user_w, item_w, g->num_users};
-    const float c0 = 1.0f / (float)((K + 1) * (K + 1));
-    if (g->num_active < g->num_nodes) {
-        fwd_inactive_kernel<<<cdiv(g->num_nodes, 2 * WARPS_PER_CTA), CTA_THREADS, 0, st>>>(
-            e0, g->active, g->num_nodes, c0, final_out, rnorm);
-        LGCN_LAUNCH_CHECK();
-    }
-    float *y[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *y[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int k = 1; k < K; ++k) y[k] = work + (size_t)(k - 1) * n * D;
+    const Range all{0, g->n_in_tasks, 0, g->num_nodes};
     for (int k = 1; k <= K; ++k) {
-        const bool first = k == 1, last = k == K;
-        if (first && last) {
-            FwdOp<true, true> op{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, nullptr, nullptr,
-                                 {nullptr, nullptr, nullptr}, 0, c0, final_out, rnorm};
-            LGCN_CUDA(launch_fwd(g, op, st));
-        } else if (first) {
-            FwdOp<true, false> op{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, nullptr, y[1],
-                                  {nullptr, nullptr, nullptr}, 0, c0, nullptr, nullptr};
-            LGCN_CUDA(launch_fwd(g, op, st));
-        } else if (!last) {
-            FwdOp<false, false> op{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, y[k - 1], y[k],
-                                   {nullptr, nullptr, nullptr}, 0, c0, nullptr, nullptr};
-            LGCN_CUDA(launch_fwd(g, op, st));
-        } else {
-            FwdOp<false, true> op{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, y[k - 1], nullptr,
-                                  {y[1], y[2], y[3]}, K - 1, c0, final_out, rnorm};
-            LGCN_CUDA(launch_fwd(g, op, st));
-        }
+        int rc = fwd_layer_impl(g, e0, k, K, true, y[k - 1], k < K ? y[k] : nullptr, y[1], y[2], y[3], final_out,
+                                rnorm, all, st);
+        if (rc) return rc;
     }
     return LGCN_OK;
 }
@@ -296,35 +337,13 @@ int propagate_bwd_impl(const lgcn_graph *g, const float *G, int K, const float *
     LGCN_REQUIRE(work_bytes >= need && (need == 0 || work), LGCN_E_WORKSPACE,
                  "propagate_bwd: workspace %zu < %zu bytes", work_bytes, need);
     const Table e0{user_w, item_w, g->num_users};
-    const float c0 = 1.0f / (float)((K + 1) * (K + 1));
-    double *ex0 = accum ? accum + 1 : nullptr, *ex1 = accum ? accum + 2 : nullptr;
-    if (g->num_active < g->num_nodes) {
-        bwd_inactive_kernel<<<cdiv(g->num_nodes, 2 * WARPS_PER_CTA), CTA_THREADS, 0, st>>>(
-            G, g->active, g->num_nodes, c0, e0, neg_count, reg_coef, g->num_users, grad, ex0, ex1);
-        LGCN_LAUNCH_CHECK();
-    }
     float *z[2] = {work, work ? work + n * D : nullptr};
+    const Range all{0, g->n_out_tasks, 0, g->num_nodes};
     for (int j = 1; j <= K; ++j) {
-        const bool first = j == 1, last = j == K;
-        const float *zin = first ? nullptr : z[j & 1];          // written by layer j-1
-        float *zout = last ? nullptr : z[(j - 1) & 1];
-        if (first && last) {
-            BwdOp<true, true> op{ex0, ex1, g->out_nbr, g->in_ptr, g->out_ptr, g->dis, G, zin, zout, c0,
-                                 grad, e0, neg_count, reg_coef, g->num_users};
-            LGCN_CUDA(launch_bwd(g, op, st));
-        } else if (first) {
-            BwdOp<true, false> op{nullptr, nullptr, g->out_nbr, g->in_ptr, g->out_ptr, g->dis, G, zin, zout,
-                                  c0, grad, e0, neg_count, reg_coef, g->num_users};
-            LGCN_CUDA(launch_bwd(g, op, st));
-        } else if (!last) {
-            BwdOp<false, false> op{nullptr, nullptr, g->out_nbr, g->in_ptr, g->out_ptr, g->dis, G, zin, zout,
-                                   c0, grad, e0, neg_count, reg_coef, g->num_users};
-            LGCN_CUDA(launch_bwd(g, op, st));
-        } else {
-            BwdOp<false, true> op{ex0, ex1, g->out_nbr, g->in_ptr, g->out_ptr, g->dis, G, zin, zout, c0,
-                                  grad, e0, neg_count, reg_coef, g->num_users};
-            LGCN_CUDA(launch_bwd(g, op, st));
-        }
+        const float *zin = j == 1 ? nullptr : z[j & 1];          // written by layer j-1
+        float *zout = j == K ? nullptr : z[(j - 1) & 1];
+        int rc = bwd_layer_impl(g, G, j, K, zin, zout, e0, neg_count, reg_coef, grad, accum, all, st);
+        if (rc) return rc;
     }
     return LGCN_OK;
 }
@@ -344,4 +363,49 @@ extern "C" int lgcn_propagate_bwd(const lgcn_graph *g, const float *grad_final, 
                                   size_t work_bytes, void *stream) {
     return lgcn::propagate_bwd_impl(g, grad_final, num_layers, user_w, item_w, neg_count, reg_coef,
                                     grad_e0, accum, work, work_bytes, (cudaStream_t)stream);
+}
+
+// ---- sharded (owner-computes-by-row-range) entry points -------------------------------------------
+
+extern "C" int lgcn_prescale(const lgcn_graph *g, const float *user_w, const float *item_w, int64_t row_begin,
+                             int64_t row_end, float *y0, void *stream) {
+    using namespace lgcn;
+    LGCN_REQUIRE(g && user_w && item_w && y0 && row_begin >= 0 && row_end <= g->num_nodes, LGCN_E_INVALID,
+                 "prescale: bad argument");
+    if (row_end <= row_begin) return LGCN_OK;
+    prescale_kernel<<<cdiv(row_end - row_begin, 2 * WARPS_PER_CTA), CTA_THREADS, 0, (cudaStream_t)stream>>>(
+        Table{user_w, item_w, g->num_users}, g->dis, (int)row_begin, (int)row_end, y0);
+    LGCN_LAUNCH_CHECK();
+    return LGCN_OK;
+}
+
+extern "C" int lgcn_fwd_layer(const lgcn_graph *g, const float *user_w, const float *item_w, int k, int num_layers,
+                              const float *yin, float *yout, const float *y1, const float *y2, const float *y3,
+                              float *final_out, float *rnorm, int task_begin, int task_end, int64_t row_begin,
+                              int64_t row_end, void *stream) {
+    using namespace lgcn;
+    LGCN_REQUIRE(g && user_w && item_w && yin && k >= 1 && k <= num_layers && num_layers <= 4, LGCN_E_INVALID,
+                 "fwd_layer: bad argument");
+    LGCN_REQUIRE(k == num_layers ? final_out != nullptr : yout != nullptr, LGCN_E_INVALID, "fwd_layer: missing output");
+    LGCN_REQUIRE(task_begin >= 0 && task_end <= g->n_in_tasks && task_begin <= task_end, LGCN_E_INVALID,
+                 "fwd_layer: task range [%d,%d) outside [0,%d)", task_begin, task_end, g->n_in_tasks);
+    return fwd_layer_impl(g, Table{user_w, item_w, g->num_users}, k, num_layers, false, yin, yout, y1, y2, y3, final_out,
+                          rnorm, Range{task_begin, task_end, (int)row_begin, (int)row_end}, (cudaStream_t)stream);
+}
+
+extern "C" int lgcn_bwd_layer(const lgcn_graph *g, const float *grad_final, int j, int num_layers, const float *zin,
+                              float *zout, const float *user_w, const float *item_w, const int32_t *neg_count,
+                              float reg_coef, float *grad_e0, double *accum, int task_begin, int task_end,
+                              int64_t row_begin, int64_t row_end, void *stream) {
+    using namespace lgcn;
+    LGCN_REQUIRE(g && grad_final && j >= 1 && j <= num_layers && num_layers <= 4, LGCN_E_INVALID, "bwd_layer: bad argument");
+    LGCN_REQUIRE(j == 1 || zin, LGCN_E_INVALID, "bwd_layer: zin missing");
+    LGCN_REQUIRE(j == num_layers ? grad_e0 != nullptr : zout != nullptr, LGCN_E_INVALID, "bwd_layer: missing output");
+    LGCN_REQUIRE(task_begin >= 0 && task_end <= g->n_out_tasks && task_begin <= task_end, LGCN_E_INVALID,
+                 "bwd_layer: task range outside the list");
+    LGCN_REQUIRE(reg_coef == 0.f || (user_w && item_w && neg_count && accum), LGCN_E_INVALID,
+                 "bwd_layer: regulariser needs weights, neg_count and accum");
+    return bwd_layer_impl(g, grad_final, j, num_layers, zin, zout, Table{user_w, item_w, g->num_users}, neg_count,
+                          reg_coef, grad_e0, accum, Range{task_begin, task_end, (int)row_begin, (int)row_end},
+                          (cudaStream_t)stream);
 }

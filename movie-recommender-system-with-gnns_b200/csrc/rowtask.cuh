@@ -32,9 +32,13 @@ template <class Item, int kUnroll = UNROLL, class Fetch, class Load, class Apply
 __device__ __forceinline__ void for_each_edge(int begin, int end, int lane, Fetch fetch, Load load,
                                               Apply apply) {
     const int half = lane >> 4;
+    // software pipeline: the (coalesced) index/metadata load of chunk c+1 is issued before the row
+    // gathers of chunk c, so its latency hides behind them instead of heading the next iteration
+    Item mine = fetch(begin + lane < end ? begin + lane : -1);
     for (int base = begin; base < end; base += 32) {
         const int n = min(32, end - base);
-        Item mine = fetch(lane < n ? base + lane : -1);
+        const int nb = base + 32 + lane;
+        Item next = fetch(nb < end ? nb : -1);
 #pragma unroll
         for (int j = 0; j < 32; j += 2 * kUnroll) {
             if (j >= n) break;                       // warp-uniform
@@ -47,6 +51,7 @@ __device__ __forceinline__ void for_each_edge(int begin, int end, int lane, Fetc
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) apply(u, it[u]);
         }
+        mine = next;
     }
 }
 

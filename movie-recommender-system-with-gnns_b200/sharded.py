@@ -1,0 +1,285 @@
+"""Node-range sharded full-graph LightGCN training step (BASELINE configs C3 / C5).
+
+One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  Every rank holds the full
+CSR pair of the edge list and executes only the warp tasks of the rows it OWNS: a contiguous user
+range plus a contiguous item range, each balanced by edge count, so that every rank gets its share
+of SpMM rows of both kinds and of BPR triplets (triplets follow their user).  Rows are
+owner-computed (no float atomics across ranks); the exchange steps are
+
+    forward   all-gather of the owned slabs of y_k = dis (.) x_k before layer k+1     (K all-gathers)
+              all-gather of the final embeddings + their inverse norms (BPR reads remote rows)
+    BPR       all-reduce(sum) of dL/dfinal [N,64] and of the negative-sample histogram
+    backward  all-gather of z_j = dis (.) h_j before layer j+1                       (K-1 all-gathers)
+    clip      all-reduce of (softplus sum, regulariser sum, ||grad||^2)              (3 doubles)
+
+Weights and Adam state are updated for owned rows only -- no parameter all-reduce; ``gather_weights``
+assembles the full tables (checkpointing).  With world_size 1 the result equals ``lgcn_train_step``.
+
+The orchestration is backend-agnostic (``ops``): ``CudaOps`` drives the C ABI; the CPU test-suite
+injects a torch stand-in to check the sharded algorithm over gloo with world_size 2.
+"""
+from __future__ import annotations
+
+from ctypes import byref
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+DIM = 64
+
+
+# ----------------------------------------------------------------------------------------------
+# ownership plan
+# ----------------------------------------------------------------------------------------------
+
+def balanced_boundaries(weight: torch.Tensor, parts: int) -> List[int]:
+    """Split [0,len) into ``parts`` contiguous ranges of near-equal total weight (prefix-sum cut)."""
+    n = weight.numel()
+    if n == 0:
+        return [0] * (parts + 1)
+    pre = torch.cumsum(weight.to(torch.float64), 0)
+    total = float(pre[-1])
+    cuts = [0]
+    for p in range(1, parts):
+        cuts.append(int(torch.searchsorted(pre, torch.tensor(total * p / parts, dtype=torch.float64))))
+    cuts.append(n)
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return cuts
+
+
+@dataclass
+class ShardPlan:
+    """Row ownership: rank r owns user rows [user_ptr[r], user_ptr[r+1]) and item rows
+    [item_ptr[r], item_ptr[r+1]) (global node ids; items start at num_users)."""
+    num_users: int
+    num_items: int
+    user_ptr: List[int]
+    item_ptr: List[int]
+
+    @property
+    def world(self) -> int:
+        return len(self.user_ptr) - 1
+
+    def segments(self, rank: int) -> List[Tuple[int, int]]:
+        return [(self.user_ptr[rank], self.user_ptr[rank + 1]), (self.item_ptr[rank], self.item_ptr[rank + 1])]
+
+    @staticmethod
+    def build(in_deg: torch.Tensor, out_deg: torch.Tensor, num_users: int, world: int, row_cost: int = 8) -> "ShardPlan":
+        w = (in_deg + out_deg + row_cost).cpu()
+        n = w.numel()
+        up = balanced_boundaries(w[:num_users], world)
+        ip = [num_users + c for c in balanced_boundaries(w[num_users:], world)]
+        return ShardPlan(num_users, n - num_users, up, ip)
+
+
+# ----------------------------------------------------------------------------------------------
+# collectives (plumbing)
+# ----------------------------------------------------------------------------------------------
+
+class Comm:
+    def __init__(self, group=None):
+        self.group = group
+        self.on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.on else 0
+        self.world = dist.get_world_size(group) if self.on else 1
+        self.backend = dist.get_backend(group) if self.on else "none"
+
+    def allgather_rows(self, buf: torch.Tensor, ptr: Sequence[int]) -> None:
+        """In place: every rank contributes buf[ptr[r]:ptr[r+1]] and receives the other slabs."""
+        if self.world == 1:
+            return
+        views = [buf[ptr[r]:ptr[r + 1]] for r in range(self.world)]
+        sizes = {v.shape[0] for v in views}
+        if self.backend == "nccl":
+            if len(sizes) == 1:
+                lo, hi = ptr[0], ptr[-1]
+                dist.all_gather_into_tensor(buf[lo:hi], views[self.rank], group=self.group)
+            else:
+                dist.all_gather(views, views[self.rank], group=self.group)   # uneven: grouped broadcasts
+        else:                                                                # gloo: equal sizes only
+            for r in range(self.world):
+                if views[r].numel():
+                    dist.broadcast(views[r], src=dist.get_global_rank(self.group, r) if self.group else r,
+                                   group=self.group)
+
+    def allreduce(self, t: torch.Tensor) -> None:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def barrier(self) -> None:
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+
+# ----------------------------------------------------------------------------------------------
+# CUDA backend
+# ----------------------------------------------------------------------------------------------
+
+class CudaOps:
+    """The product backend: each method is one C-ABI call on the rank's row / task ranges."""
+
+    def __init__(self, edge_index: torch.Tensor, num_users: int, num_items: int, num_layers: int,
+                 lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0):
+        from . import _lib
+        self._lib = _lib
+        self.L = _lib.lib()
+        self.dev = edge_index.device
+        self.g = _lib.Graph(edge_index, num_users, num_items)
+        self.nu, self.ni, self.n, self.k = num_users, num_items, num_users + num_items, num_layers
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        n = self.n
+        self.y = [torch.zeros(n, DIM, **f32) for _ in range(num_layers)]        # y_0 .. y_{K-1}
+        self.z = [torch.zeros(n, DIM, **f32) for _ in range(min(2, max(num_layers - 1, 0)))]
+        self.final = torch.zeros(n, DIM, **f32)
+        self.rnorm = torch.zeros(n, **f32)
+        self.G = torch.zeros(n, DIM, **f32)
+        self.grad = torch.zeros(n, DIM, **f32)
+        self.neg_count = torch.zeros(num_items, dtype=torch.int32, device=self.dev)
+        self.scratch = torch.empty(2 * max(self.g.num_triplets, 1), **f32)
+        self.accum = torch.zeros(4, dtype=torch.float64, device=self.dev)
+        self.loss = torch.zeros(1, **f32)
+        self.m, self.v = torch.zeros(n, DIM, **f32), torch.zeros(n, DIM, **f32)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        c = _lib.CAdam()
+        c.lr, c.beta1, c.beta2, c.eps, c.max_norm = lr, betas[0], betas[1], eps, max_norm
+        c.step, c.m, c.v = self.step_count.data_ptr(), self.m.data_ptr(), self.v.data_ptr()
+        self.adam = c
+        self.in_rows = self.g.in_tasks.view(-1, 8)[: self.g.c.n_in_tasks, 0].cpu()
+        self.out_rows = self.g.out_tasks.view(-1, 8)[: self.g.c.n_out_tasks, 0].cpu()
+
+    # -- graph facts the planner needs
+    @property
+    def num_triplets(self) -> int:
+        return self.g.num_triplets
+
+    def degrees(self):
+        return self.g.in_degree(), self.g.out_degree()
+
+    def _tasks(self, rows: torch.Tensor, rb: int, re: int) -> Tuple[int, int]:
+        b = int(torch.searchsorted(rows, torch.tensor(rb, dtype=rows.dtype)))
+        e = int(torch.searchsorted(rows, torch.tensor(re, dtype=rows.dtype)))
+        return b, e
+
+    def set_weights(self, user_w: torch.Tensor, item_w: torch.Tensor) -> None:
+        self.uw, self.iw = user_w, item_w
+
+    def _s(self):
+        return self._lib.stream_ptr(self.dev)
+
+    def step_begin(self):
+        self._lib.check(self.L.lgcn_step_begin(byref(self.adam), self.accum.data_ptr(), self._s()))
+
+    def prescale(self, rb, re):
+        self._lib.check(self.L.lgcn_prescale(self.g.ref, self.uw.data_ptr(), self.iw.data_ptr(), rb, re,
+                                             self.y[0].data_ptr(), self._s()))
+
+    def fwd_layer(self, k, rb, re):
+        tb, te = self._tasks(self.in_rows, rb, re)
+        last = k == self.k
+        ys = [self.y[i].data_ptr() if i < self.k else None for i in (1, 2, 3)]
+        self._lib.check(self.L.lgcn_fwd_layer(
+            self.g.ref, self.uw.data_ptr(), self.iw.data_ptr(), k, self.k, self.y[k - 1].data_ptr(),
+            None if last else self.y[k].data_ptr(), ys[0], ys[1], ys[2],
+            self.final.data_ptr() if last else None, self.rnorm.data_ptr() if last else None, tb, te, rb, re, self._s()))
+
+    def bpr(self, neg, urb, ure):
+        tb, te = self._tasks(self.out_rows, urb, ure)
+        self._lib.check(self.L.lgcn_bpr_fwd_bwd_range(
+            self.g.ref, self.final.data_ptr(), self.rnorm.data_ptr(), neg.data_ptr(), self.G.data_ptr(),
+            self.neg_count.data_ptr(), self.scratch.data_ptr(), self.accum.data_ptr(), tb, te, urb, ure, self._s()))
+
+    def bwd_layer(self, j, rb, re, bpr_coeff):
+        tb, te = self._tasks(self.out_rows, rb, re)
+        last = j == self.k
+        zin = None if j == 1 else self.z[j & 1].data_ptr()
+        zout = None if last else self.z[(j - 1) & 1].data_ptr()
+        reg = 2.0 * bpr_coeff / (64.0 * self.g.num_triplets)
+        self._lib.check(self.L.lgcn_bwd_layer(
+            self.g.ref, self.G.data_ptr(), j, self.k, zin, zout, self.uw.data_ptr(), self.iw.data_ptr(),
+            self.neg_count.data_ptr(), reg, self.grad.data_ptr() if last else None, self.accum.data_ptr(),
+            tb, te, rb, re, self._s()))
+
+    def zbuf(self, j):
+        return self.z[(j - 1) & 1]
+
+    def clip_adam(self, rb, re, bpr_coeff):
+        self._lib.check(self.L.lgcn_clip_adam_rows(
+            byref(self.adam), self.uw.data_ptr(), self.iw.data_ptr(), self.nu, self.ni, self.grad.data_ptr(),
+            self.accum.data_ptr(), self.g.num_triplets, bpr_coeff, self.loss.data_ptr(), rb, re, self._s()))
+
+
+# ----------------------------------------------------------------------------------------------
+# orchestration
+# ----------------------------------------------------------------------------------------------
+
+class ShardedTrainer:
+    """Full-graph training step of utils/train_test.py:88-96, node-range sharded."""
+
+    def __init__(self, ops, user_w: torch.Tensor, item_w: torch.Tensor, comm: Optional[Comm] = None,
+                 bpr_coeff: float = 5e-3, plan: Optional[ShardPlan] = None):
+        self.ops = ops
+        self.comm = comm if comm is not None else Comm()
+        self.bpr_coeff = bpr_coeff
+        self.user_w, self.item_w = user_w, item_w
+        ops.set_weights(user_w, item_w)
+        ind, outd = ops.degrees()
+        self.plan = plan if plan is not None else ShardPlan.build(ind, outd, ops.nu, self.comm.world)
+        self.segs = self.plan.segments(self.comm.rank)
+        self.k = ops.k
+
+    def _gather(self, buf: torch.Tensor) -> None:
+        self.comm.allgather_rows(buf, self.plan.user_ptr)
+        self.comm.allgather_rows(buf, self.plan.item_ptr)
+
+    def step(self, neg: torch.Tensor) -> torch.Tensor:
+        """One step; ``neg`` is the FULL [P] negative vector (identical on every rank; each rank reads
+        the entries of its own triplets).  Returns the loss as a device tensor (same on every rank)."""
+        o, k = self.ops, self.k
+        o.step_begin()
+        for rb, re in self.segs:
+            o.prescale(rb, re)
+        self._gather(o.y[0])
+        for layer in range(1, k + 1):
+            for rb, re in self.segs:
+                o.fwd_layer(layer, rb, re)
+            if layer < k:
+                self._gather(o.y[layer])
+        self._gather(o.final)
+        self._gather(o.rnorm)
+        urb, ure = self.segs[0]
+        o.bpr(neg, urb, ure)
+        self.comm.allreduce(o.G)
+        self.comm.allreduce(o.neg_count)
+        for j in range(1, k + 1):
+            for rb, re in self.segs:
+                o.bwd_layer(j, rb, re, self.bpr_coeff)
+            if j < k:
+                self._gather(o.zbuf(j))
+        self.comm.allreduce(o.accum)
+        for rb, re in self.segs:
+            o.clip_adam(rb, re, self.bpr_coeff)
+        return o.loss
+
+    def gather_weights(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Full, up-to-date tables on every rank (for state_dict / best_model.pth)."""
+        nu = self.plan.num_users
+        full = torch.cat([self.user_w, self.item_w])
+        self._gather(full)
+        return full[:nu].clone(), full[nu:].clone()
+
+    def propagate_only(self) -> torch.Tensor:
+        """Forward propagation alone (BASELINE config C3's per-layer timing): returns final [N,64]."""
+        o, k = self.ops, self.k
+        for rb, re in self.segs:
+            o.prescale(rb, re)
+        self._gather(o.y[0])
+        for layer in range(1, k + 1):
+            for rb, re in self.segs:
+                o.fwd_layer(layer, rb, re)
+            if layer < k:
+                self._gather(o.y[layer])
+        self._gather(o.final)
+        return o.final
