@@ -44,7 +44,10 @@ extern "C" {
 #endif
 
 #define LGCN_DIM 64
-#define LGCN_ROW_SPLIT 512          /* max edges handled by one warp task                */
+#define LGCN_ROW_SPLIT 512          /* max edges handled by one warp task (large graphs)  */
+#define LGCN_ROW_SPLIT_SMALL 64     /* same, for edge lists below LGCN_SMALL_GRAPH edges: the longest
+                                       task is the critical path of a launch-sized Cluster-GCN batch */
+#define LGCN_SMALL_GRAPH (1 << 20)
 
 #define LGCN_OK 0
 #define LGCN_E_INVALID   (-1)       /* bad argument (null pointer, negative size, K<1 ...) */
@@ -82,7 +85,8 @@ typedef struct lgcn_graph {
     float *partials;                 /* [max(n_in_slots,n_out_slots) * 80] scratch            */
     int32_t *slot_counters;          /* [max slots] zero between launches                     */
     int32_t num_active;              /* nodes with active[n] == 1                             */
-    int32_t pad;
+    int32_t row_split;               /* max edges per task used for this graph                */
+    const int32_t *active_list;      /* [num_active] ascending ids of the active nodes        */
 } lgcn_graph;
 
 /* ---- K0: graph build ------------------------------------------------------------------ */
@@ -97,6 +101,7 @@ typedef struct lgcn_graph_sizes {
     size_t partial_bytes;  /* upper bound for partials                             */
     size_t counter_bytes;  /* upper bound for slot_counters                        */
     size_t workspace_bytes;/* temporary storage for lgcn_graph_build               */
+    size_t active_list_bytes; /* N int32                                            */
 } lgcn_graph_sizes;
 
 int lgcn_graph_sizes_query(int64_t num_nodes, int64_t num_edges, lgcn_graph_sizes *out);
@@ -160,6 +165,13 @@ typedef struct lgcn_adam {
     double lr, beta1, beta2, eps, max_norm;   /* doubles: torch derives 1-beta, lr/(1-beta^t) in double */
     int64_t *step;          /* device int64: incremented by lgcn_step_begin             */
     float *m, *v;           /* [N,64] exp_avg / exp_avg_sq                              */
+    /* optional: bias-correction table computed by the host exactly as torch does (Python doubles):
+     * bc_table[2t] = lr/(1-beta1^t), bc_table[2t+1] = sqrt(1-beta2^t) for t < bc_len (device floats).
+     * Steps beyond the table fall back to in-kernel pow(). */
+    const float *bc_table;
+    int64_t bc_len;
+    /* optional (sparse steps only): row_step[r] = last optimiser step applied to row r (device) */
+    int32_t *row_step;
 } lgcn_adam;
 
 /* Zeroes accum[0..3] and increments *opt->step (one tiny launch). */
@@ -212,6 +224,10 @@ typedef struct lgcn_step_buffers {
     int32_t *neg_count;    /* [I]    */
     float *trip_scratch;   /* [2*Pmax] */
     double *accum;         /* [4]    */
+    /* sparse steps only */
+    int32_t *neg_flag;     /* [I] zero-initialised: last step in which the item was a negative */
+    int32_t *neg_list;     /* [I] distinct INACTIVE negative items of the current step          */
+    int32_t *neg_list_count; /* [1]                                                              */
 } lgcn_step_buffers;
 
 /* utils/train_test.py:88-96 for one batch: forward, BPR loss, backward, clip, Adam.
@@ -220,6 +236,20 @@ typedef struct lgcn_step_buffers {
 int lgcn_train_step(const lgcn_graph *g, float *user_w, float *item_w, int num_layers,
                     const int64_t *neg, float bpr_coeff, const lgcn_adam *opt,
                     const lgcn_step_buffers *buf, float *loss_out, void *stream);
+
+/* Same step, work proportional to the rows the batch TOUCHES (nodes with an incident edge + sampled
+ * negatives) instead of N: identical arithmetic, but rows the batch does not touch are not visited --
+ * their (zero-gradient) Adam updates are replayed exactly, per row, the next time the row is touched
+ * (opt->row_step) or by lgcn_adam_flush.  For Cluster-GCN batches, where the reference pays full-table
+ * passes per batch.  Requires opt->row_step, opt->bc_table, buf->neg_*;
+ * buf->grad_final and buf->neg_count must be all-zero on entry and are all-zero again on exit. */
+int lgcn_train_step_sparse(const lgcn_graph *g, float *user_w, float *item_w, int num_layers,
+                           const int64_t *neg, float bpr_coeff, const lgcn_adam *opt,
+                           const lgcn_step_buffers *buf, float *loss_out, void *stream);
+
+/* Brings every row up to the current step (replays the pending zero-gradient updates). */
+int lgcn_adam_flush(const lgcn_adam *opt, float *user_w, float *item_w, int64_t num_users,
+                    int64_t num_items, void *stream);
 
 /* Loss only (evaluate(), utils/train_test.py:153-156): forward + BPR value, no gradients. */
 int lgcn_eval_loss(const lgcn_graph *g, const float *user_w, const float *item_w, int num_layers,

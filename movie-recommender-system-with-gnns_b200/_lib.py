@@ -27,7 +27,7 @@ EXPORTS = [
     "lgcn_clip_adam", "lgcn_train_step", "lgcn_eval_loss", "lgcn_partition_metis",
     "lgcn_cluster_extract_workspace_bytes", "lgcn_cluster_extract", "lgcn_score_topk",
     "lgcn_spmm", "lgcn_bpr_rows", "lgcn_prescale", "lgcn_fwd_layer", "lgcn_bwd_layer",
-    "lgcn_bpr_fwd_bwd_range", "lgcn_clip_adam_rows",
+    "lgcn_bpr_fwd_bwd_range", "lgcn_clip_adam_rows", "lgcn_train_step_sparse", "lgcn_adam_flush",
 ]
 
 
@@ -49,24 +49,26 @@ class CGraph(Structure):
         ("n_in_user_tasks", c_int32), ("n_out_user_tasks", c_int32),
         ("n_in_slots", c_int32), ("n_out_slots", c_int32),
         ("partials", c_void_p), ("slot_counters", c_void_p),
-        ("num_active", c_int32), ("pad", c_int32),
+        ("num_active", c_int32), ("row_split", c_int32), ("active_list", c_void_p),
     ]
 
 
 class CGraphSizes(Structure):
     _fields_ = [(n, c_size_t) for n in ("ptr_bytes", "nbr_bytes", "dis_bytes", "active_bytes", "task_bytes",
-                                        "partial_bytes", "counter_bytes", "workspace_bytes")]
+                                        "partial_bytes", "counter_bytes", "workspace_bytes", "active_list_bytes")]
 
 
 class CAdam(Structure):
     _fields_ = [("lr", c_double), ("beta1", c_double), ("beta2", c_double), ("eps", c_double),
-                ("max_norm", c_double), ("step", c_void_p), ("m", c_void_p), ("v", c_void_p)]
+                ("max_norm", c_double), ("step", c_void_p), ("m", c_void_p), ("v", c_void_p),
+                ("bc_table", c_void_p), ("bc_len", c_int64), ("row_step", c_void_p)]
 
 
 class CStepBuffers(Structure):
     _fields_ = [("final_emb", c_void_p), ("rnorm", c_void_p), ("grad_final", c_void_p), ("grad_e0", c_void_p),
                 ("work", c_void_p), ("work_bytes", c_size_t), ("neg_count", c_void_p),
-                ("trip_scratch", c_void_p), ("accum", c_void_p)]
+                ("trip_scratch", c_void_p), ("accum", c_void_p),
+                ("neg_flag", c_void_p), ("neg_list", c_void_p), ("neg_list_count", c_void_p)]
 
 
 _lib = None
@@ -115,6 +117,8 @@ def lib():
     L.lgcn_bpr_fwd_bwd_range.argtypes = [POINTER(CGraph)] + [c_void_p] * 7 + [c_int, c_int, c_int64, c_int64, c_void_p]
     L.lgcn_clip_adam_rows.argtypes = [POINTER(CAdam), c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                       c_float, c_void_p, c_int64, c_int64, c_void_p]
+    L.lgcn_train_step_sparse.argtypes = L.lgcn_train_step.argtypes
+    L.lgcn_adam_flush.argtypes = [POINTER(CAdam), c_void_p, c_void_p, c_int64, c_int64, c_void_p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("lgcn_last_error", "lgcn_cluster_extract_workspace_bytes"):
@@ -174,6 +178,7 @@ class Graph:
         self.out_tasks = torch.empty(sz.task_bytes // 4, **i32)
         self.partials = torch.empty(sz.partial_bytes // 4, dtype=torch.float32, device=dev)
         self.slot_counters = torch.empty(sz.counter_bytes // 4, **i32)
+        self.active_list = torch.empty(n, **i32)
         ws = torch.empty(sz.workspace_bytes, dtype=torch.uint8, device=dev)
         c = CGraph()
         c.in_ptr, c.in_nbr, c.in_trip = self.in_ptr.data_ptr(), self.in_nbr.data_ptr(), self.in_trip.data_ptr()
@@ -181,6 +186,7 @@ class Graph:
         c.dis, c.active = self.dis.data_ptr(), self.active.data_ptr()
         c.in_tasks, c.out_tasks = self.in_tasks.data_ptr(), self.out_tasks.data_ptr()
         c.partials, c.slot_counters = self.partials.data_ptr(), self.slot_counters.data_ptr()
+        c.active_list = self.active_list.data_ptr()
         check(L.lgcn_graph_build(ei.data_ptr(), e, n, num_users, byref(c), ws.data_ptr(), ws.numel(),
                                  stream_ptr(dev)))
         del ws
@@ -190,6 +196,8 @@ class Graph:
         nslots = max(c.n_in_slots, c.n_out_slots, 1)
         self.partials = torch.empty(nslots * PARTIAL_STRIDE, dtype=torch.float32, device=dev)
         self.slot_counters = torch.zeros(nslots, **i32)
+        self.active_list = self.active_list[: max(c.num_active, 1)].clone()
+        c.active_list = self.active_list.data_ptr()
         c.in_tasks, c.out_tasks = self.in_tasks.data_ptr(), self.out_tasks.data_ptr()
         c.partials, c.slot_counters = self.partials.data_ptr(), self.slot_counters.data_ptr()
         self.c = c
@@ -222,6 +230,11 @@ class StepBuffers:
         self.neg_count = torch.zeros(num_items, dtype=torch.int32, device=device)
         self.accum = torch.zeros(4, dtype=torch.float64, device=device)
         self.trip_scratch = torch.empty(2, **f32)
+        # sparse steps: per-item stamp / list of the distinct inactive negatives of the current step
+        self.neg_flag = torch.zeros(num_items, dtype=torch.int32, device=device)
+        self.neg_list = torch.zeros(num_items, dtype=torch.int32, device=device)
+        self.neg_list_count = torch.zeros(1, dtype=torch.int32, device=device)
+        self.grad_final.zero_()            # the sparse step keeps dL/dfinal all-zero between steps
         self.c = CStepBuffers()
         self._fill()
 
@@ -232,6 +245,8 @@ class StepBuffers:
         c.work, c.work_bytes = self.work.data_ptr(), self.work.numel() * 4
         c.neg_count, c.accum = self.neg_count.data_ptr(), self.accum.data_ptr()
         c.trip_scratch = self.trip_scratch.data_ptr()
+        c.neg_flag, c.neg_list = self.neg_flag.data_ptr(), self.neg_list.data_ptr()
+        c.neg_list_count = self.neg_list_count.data_ptr()
 
     def ensure_triplets(self, p: int):
         if self.trip_scratch.numel() < 2 * p:

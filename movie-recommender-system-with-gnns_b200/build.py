@@ -21,9 +21,9 @@ CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 METIS_A = os.path.join(CUDA_HOME, "targets", "x86_64-linux", "lib", "libmetis_static.a")
 
-CU_SOURCES = ["api.cu", "graph_build.cu", "propagate.cu", "bpr.cu", "adam.cu", "cluster.cu", "score_topk.cu", "rows.cu"]
+CU_SOURCES = ["api.cu", "graph_build.cu", "propagate.cu", "bpr.cu", "adam.cu", "cluster.cu", "score_topk.cu", "rows.cu", "sparse_step.cu"]
 C_SOURCES = ["partition_metis.c"]
-HEADERS = ["common.cuh", "rowtask.cuh"]
+HEADERS = ["common.cuh", "rowtask.cuh", "adam.cuh"]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", INCLUDE, "-I", CSRC]

@@ -7,34 +7,24 @@
 //     p = p - (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 // and it is DENSE on purpose: rows with zero gradient still move through their momentum
 // (SURVEY.md App. B #11).  HBM-streaming kernel: 4 reads + 3 writes of N*256 B.
-#include "common.cuh"
-#include <math.h>
+#include "adam.cuh"
 
 namespace lgcn {
 
-__global__ void step_begin_kernel(int64_t *step, double *accum) {
+__global__ void step_begin_kernel(int64_t *step, double *accum, int32_t *list_count) {
     if (step) step[0] += 1;
     accum[0] = 0.0; accum[1] = 0.0; accum[2] = 0.0; accum[3] = 0.0;
+    if (list_count) list_count[0] = 0;
 }
 
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float4 *__restrict__ user_w, float4 *__restrict__ item_w, size_t user_vec, size_t vec_begin,
-                 size_t total_vec,
-                 const float4 *__restrict__ grad, float4 *__restrict__ m, float4 *__restrict__ v,
-                 const double *__restrict__ accum, const int64_t *__restrict__ step, double lr_d, double beta1_d,
-                 double beta2_d, double eps_d, double max_norm_d, int64_t P, float coeff, float *loss_out) {
-    // per-thread scalars (same value in every thread; cheap next to the streaming loop)
-    // scalars follow torch's _single_tensor_adam: Python-double arithmetic, then one cast to fp32
-    const double t = (double)step[0];
-    const double bc1 = 1.0 - pow(beta1_d, t);
-    const double bc2 = 1.0 - pow(beta2_d, t);
-    const float step_size = (float)(lr_d / bc1);
-    const float beta2 = (float)beta2_d, eps = (float)eps_d, max_norm = (float)max_norm_d;
-    const float bc2_sqrt = (float)sqrt(bc2);
-    const float total_norm = (float)sqrt(accum[2]);
-    float clip = max_norm > 0.f ? max_norm / (total_norm + 1e-6f) : 1.0f;   // max_norm <= 0: no clipping
-    clip = fminf(clip, 1.0f);
-    const float w1 = (float)(1.0 - beta1_d), w2 = (float)(1.0 - beta2_d);
+                 size_t total_vec, const float4 *__restrict__ grad, float4 *__restrict__ m, float4 *__restrict__ v,
+                 const double *__restrict__ accum, const int64_t *__restrict__ step, AdamHyper h, int64_t P,
+                 float coeff, float *loss_out, int32_t *__restrict__ row_step) {
+    const AdamScalars a = adam_scalars(h, step[0]);
+    const int t32 = (int)step[0];
+    const float clip = clip_coef(h, accum[2]);
     if (loss_out && blockIdx.x == 0 && threadIdx.x == 0) {
         const double p = (double)P;
         loss_out[0] = (float)(-accum[0] / (10.0 * p) + (double)coeff * accum[1] / (64.0 * p));
@@ -44,17 +34,9 @@ clip_adam_kernel(float4 *__restrict__ user_w, float4 *__restrict__ item_w, size_
         float4 *pp = i < user_vec ? user_w + i : item_w + (i - user_vec);
         const float4 g4 = __ldcs(grad + i);
         float4 p4 = *pp, m4 = m[i], v4 = v[i];
-        float *p = &p4.x, *mm = &m4.x, *vv = &v4.x;
-        const float *g = &g4.x;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float gc = g[c] * clip;
-            mm[c] = mm[c] + w1 * (gc - mm[c]);                    // exp_avg.lerp_(grad, 1-beta1)
-            vv[c] = vv[c] * beta2 + w2 * gc * gc;                 // mul_(beta2).addcmul_(g, g, 1-beta2)
-            const float denom = sqrtf(vv[c]) / bc2_sqrt + eps;
-            p[c] = p[c] - step_size * (mm[c] / denom);            // addcdiv_(m, denom, -step_size)
-        }
+        adam_vec(p4, m4, v4, g4, clip, a);
         *pp = p4; m[i] = m4; v[i] = v4;
+        if (row_step && (i % D4) == 0) row_step[i / D4] = t32;     // every row is now at step t
     }
 }
 
@@ -62,7 +44,7 @@ clip_adam_kernel(float4 *__restrict__ user_w, float4 *__restrict__ item_w, size_
 
 extern "C" int lgcn_step_begin(const lgcn_adam *opt, double *accum, void *stream) {
     LGCN_REQUIRE(accum, LGCN_E_INVALID, "step_begin: null accum");
-    lgcn::step_begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(opt ? opt->step : nullptr, accum);
+    lgcn::step_begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(opt ? opt->step : nullptr, accum, nullptr);
     LGCN_LAUNCH_CHECK();
     return LGCN_OK;
 }
@@ -89,8 +71,8 @@ extern "C" int lgcn_clip_adam_rows(const lgcn_adam *opt, float *user_w, float *i
     lgcn::clip_adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<float4 *>(user_w), reinterpret_cast<float4 *>(item_w), user_vec, vb, ve,
         reinterpret_cast<const float4 *>(grad), reinterpret_cast<float4 *>(opt->m),
-        reinterpret_cast<float4 *>(opt->v), accum, opt->step, opt->lr, opt->beta1, opt->beta2, opt->eps,
-        opt->max_norm, num_triplets, bpr_coeff, loss_out);
+        reinterpret_cast<float4 *>(opt->v), accum, opt->step, lgcn::make_hyper(opt), num_triplets, bpr_coeff, loss_out,
+        opt->row_step);
     LGCN_LAUNCH_CHECK();
     return LGCN_OK;
 }

@@ -1,0 +1,64 @@
+// Shared Adam arithmetic: the dense streaming kernel (adam.cu) and the row-list / replay kernels of
+// the sparse step (sparse_step.cu) must produce bit-identical updates, so both go through these.
+#pragma once
+#include "common.cuh"
+#include <math.h>
+
+namespace lgcn {
+
+struct AdamHyper {            // by-value kernel argument
+    double lr, beta1, beta2, eps, max_norm;
+    const float *bc_table;    // [2*bc_len]: (lr/(1-b1^t), sqrt(1-b2^t)) or null
+    long long bc_len;
+};
+
+static inline AdamHyper make_hyper(const lgcn_adam *o) {
+    return AdamHyper{o->lr, o->beta1, o->beta2, o->eps, o->max_norm, o->bc_table, (long long)o->bc_len};
+}
+
+struct AdamScalars {
+    float step_size, bc2_sqrt, beta2, eps, w1, w2;
+};
+
+// torch.optim.Adam (_single_tensor_adam): scalars in Python-double arithmetic, one cast to fp32.
+__device__ __forceinline__ AdamScalars adam_scalars(const AdamHyper &h, long long t) {
+    AdamScalars a;
+    if (h.bc_table && t < h.bc_len) {
+        a.step_size = __ldg(h.bc_table + 2 * t);
+        a.bc2_sqrt = __ldg(h.bc_table + 2 * t + 1);
+    } else {
+        const double bc1 = 1.0 - pow(h.beta1, (double)t), bc2 = 1.0 - pow(h.beta2, (double)t);
+        a.step_size = (float)(h.lr / bc1);
+        a.bc2_sqrt = (float)sqrt(bc2);
+    }
+    a.beta2 = (float)h.beta2;
+    a.eps = (float)h.eps;
+    a.w1 = (float)(1.0 - h.beta1);
+    a.w2 = (float)(1.0 - h.beta2);
+    return a;
+}
+
+__device__ __forceinline__ float clip_coef(const AdamHyper &h, double grad_norm_sq) {
+    const float max_norm = (float)h.max_norm;
+    const float total_norm = (float)sqrt(grad_norm_sq);
+    const float c = max_norm > 0.f ? max_norm / (total_norm + 1e-6f) : 1.0f;     // max_norm <= 0: no clipping
+    return fminf(c, 1.0f);
+}
+
+// one element, one step; gc = clipped gradient
+__device__ __forceinline__ void adam_elem(float &p, float &m, float &v, float gc, const AdamScalars &a) {
+    m = m + a.w1 * (gc - m);                         // exp_avg.lerp_(grad, 1-beta1)
+    v = v * a.beta2 + a.w2 * gc * gc;                // mul_(beta2).addcmul_(g, g, 1-beta2)
+    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+    p = p - a.step_size * (m / denom);               // addcdiv_(m, denom, -step_size)
+}
+
+__device__ __forceinline__ void adam_vec(float4 &p, float4 &m, float4 &v, const float4 &g, float clip,
+                                         const AdamScalars &a) {
+    adam_elem(p.x, m.x, v.x, g.x * clip, a);
+    adam_elem(p.y, m.y, v.y, g.y * clip, a);
+    adam_elem(p.z, m.z, v.z, g.z * clip, a);
+    adam_elem(p.w, m.w, v.w, g.w * clip, a);
+}
+
+}  // namespace lgcn

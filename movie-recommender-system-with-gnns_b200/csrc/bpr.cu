@@ -39,7 +39,9 @@ struct TripItemA {
     }
 };
 
-template <bool kGrad>
+// kSparse: F / rnorm only hold the ACTIVE rows; a sampled negative without any incident edge has
+// final = e0 / (K+1)^2 (every propagated layer is zero), formed on the fly.
+template <bool kGrad, bool kSparse = false>
 struct BprUserOp {
     static constexpr bool kExtras = true;
     double *extra0, *extra1;            // extra0: sum_t softplus(10 (cos+ - cos-))
@@ -51,6 +53,9 @@ struct BprUserOp {
     float *G;
     int32_t *neg_count;
     float *scratch;
+    const uint8_t *active;
+    Table e0;
+    float c0;
 
     __device__ __forceinline__ void accumulate(int row, int begin, int end, int lane, float4 &acc,
                                                float &sc, float &ex0, float &) const {
@@ -70,18 +75,24 @@ struct BprUserOp {
                     it.t = __ldg(out_trip + e);
                     it.ng = (int)__ldg(neg + it.t) + num_users;
                     it.rp = __ldg(rnorm + it.dst);
-                    it.rn = __ldg(rnorm + it.ng);
+                    if (kSparse && !__ldg(active + it.ng)) it.rn = -1.f;      // formed in `apply`
+                    else it.rn = __ldg(rnorm + it.ng);
                 }
                 return it;
             },
             [&](int, TripItemA &it) {
                 if (it.dst >= 0) {
                     it.vp = ldg4(F4 + (size_t)it.dst * D4 + l16);
-                    it.vn = ldg4(F4 + (size_t)it.ng * D4 + l16);
+                    if (kSparse && it.rn < 0.f) it.vn = f4scale(c0, ldg4(e0.row4(it.ng) + l16));
+                    else it.vn = ldg4(F4 + (size_t)it.ng * D4 + l16);
                 }
             },
             [&](int, TripItemA &it) {
                 const bool valid = it.dst >= 0;
+                if constexpr (kSparse) {
+                    const float n2 = half_sum(f4dot(it.vn, it.vn));
+                    if (it.rn < 0.f) it.rn = 1.0f / sqrtf(n2);
+                }
                 const float cp = half_sum(f4dot(fu, it.vp)) * it.rp;
                 const float cn = half_sum(f4dot(fu, it.vn)) * it.rn;
                 const float x = 10.f * (cp - cn);
@@ -238,16 +249,31 @@ int bpr_impl(const lgcn_graph *g, const float *F, const float *rnorm, const int6
     if (grad) {
         LGCN_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)g->num_nodes * D, st));
         BprUserOp<true> a{accum, nullptr, g->out_nbr, g->out_trip, neg, F, rnorm, g->num_users, invP, G,
-                          neg_count, scratch};
+                          neg_count, scratch, nullptr, Table{}, 0.f};
         LGCN_CUDA(launch_rowtasks(a, g->out_tasks, utb, ute, g->partials, g->slot_counters, st));
         BprItemOp b{nullptr, nullptr, g->in_nbr, g->in_trip, F, rnorm, scratch, invP, G, urb, ure};
         LGCN_CUDA(launch_rowtasks(b, g->in_tasks, g->n_in_user_tasks, g->n_in_tasks, g->partials,
                                   g->slot_counters, st));
     } else {
         BprUserOp<false> a{accum, nullptr, g->out_nbr, g->out_trip, neg, F, rnorm, g->num_users, invP,
-                           nullptr, neg_count, nullptr};
+                           nullptr, neg_count, nullptr, nullptr, Table{}, 0.f};
         LGCN_CUDA(launch_rowtasks(a, g->out_tasks, utb, ute, g->partials, g->slot_counters, st));
     }
+    return LGCN_OK;
+}
+
+// Sparse-step BPR: G and neg_count are all-zero on entry (invariant kept by the sparse step), F / rnorm
+// are only valid for active rows.
+int bpr_sparse_impl(const lgcn_graph *g, const float *F, const float *rnorm, const int64_t *neg, float *G,
+                    int32_t *neg_count, float *scratch, double *accum, const float *user_w, const float *item_w,
+                    int K, cudaStream_t st) {
+    const float invP = 1.0f / (float)g->num_triplets;
+    const float c0 = 1.0f / (float)((K + 1) * (K + 1));
+    BprUserOp<true, true> a{accum, nullptr, g->out_nbr, g->out_trip, neg, F, rnorm, g->num_users, invP, G,
+                            neg_count, scratch, g->active, Table{user_w, item_w, g->num_users}, c0};
+    LGCN_CUDA(launch_rowtasks(a, g->out_tasks, 0, g->n_out_user_tasks, g->partials, g->slot_counters, st));
+    BprItemOp b{nullptr, nullptr, g->in_nbr, g->in_trip, F, rnorm, scratch, invP, G, 0, g->num_users};
+    LGCN_CUDA(launch_rowtasks(b, g->in_tasks, g->n_in_user_tasks, g->n_in_tasks, g->partials, g->slot_counters, st));
     return LGCN_OK;
 }
 

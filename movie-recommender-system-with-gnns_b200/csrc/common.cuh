@@ -50,6 +50,13 @@ struct Table {
     }
 };
 
+// tasks [tb,te) of a row-sorted task list and the node rows [rb,re) they cover; inactive_rows: also
+// produce the rows without any incident edge (dense semantics) -- false in the sparse step.
+struct Range {
+    int tb, te, rb, re;
+    bool inactive_rows;
+};
+
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void f4add(float4 &a, const float4 &b) {

@@ -62,9 +62,9 @@ __global__ void ptr_kernel(const int *__restrict__ keys_sorted, int64_t E, int64
 }
 
 __global__ void node_kernel(const int *__restrict__ in_ptr, const int *__restrict__ out_ptr, int64_t N,
-                            float *__restrict__ dis, uint8_t *__restrict__ active, int *__restrict__ cnt_in,
-                            int *__restrict__ slot_in, int *__restrict__ cnt_out, int *__restrict__ slot_out,
-                            int *__restrict__ act32) {
+                            int split, float *__restrict__ dis, uint8_t *__restrict__ active,
+                            int *__restrict__ cnt_in, int *__restrict__ slot_in, int *__restrict__ cnt_out,
+                            int *__restrict__ slot_out, int *__restrict__ act32) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n > N) return;
     if (n == N) { cnt_in[n] = slot_in[n] = cnt_out[n] = slot_out[n] = act32[n] = 0; return; }
@@ -74,7 +74,7 @@ __global__ void node_kernel(const int *__restrict__ in_ptr, const int *__restric
     const int a = (din > 0 || dout > 0) ? 1 : 0;
     active[n] = (uint8_t)a;
     act32[n] = a;
-    const int pin = (din + LGCN_ROW_SPLIT - 1) / LGCN_ROW_SPLIT, pout = (dout + LGCN_ROW_SPLIT - 1) / LGCN_ROW_SPLIT;
+    const int pin = (din + split - 1) / split, pout = (dout + split - 1) / split;
     cnt_in[n] = a ? max(1, pin) : 0;
     cnt_out[n] = a ? max(1, pout) : 0;
     slot_in[n] = pin > 1 ? pin : 0;
@@ -82,7 +82,7 @@ __global__ void node_kernel(const int *__restrict__ in_ptr, const int *__restric
 }
 
 __global__ void task_kernel(const int *__restrict__ ptr, const int *__restrict__ task_off,
-                            const int *__restrict__ slot_off, int64_t N, lgcn_task *__restrict__ tasks) {
+                            const int *__restrict__ slot_off, int64_t N, int split, lgcn_task *__restrict__ tasks) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const int cnt = task_off[n + 1] - task_off[n];
@@ -95,9 +95,16 @@ __global__ void task_kernel(const int *__restrict__ ptr, const int *__restrict__
     }
     const int s0 = slot_off[n];
     for (int i = 0; i < cnt; ++i) {
-        const int tb = b + i * LGCN_ROW_SPLIT;
-        t[i] = lgcn_task{(int)n, tb, min(e, tb + LGCN_ROW_SPLIT), s0 + i, i, cnt, 0, 0};
+        const int tb = b + i * split;
+        t[i] = lgcn_task{(int)n, tb, min(e, tb + split), s0 + i, i, cnt, 0, 0};
     }
+}
+
+// active_list[rank of n among active nodes] = n   (act_off = exclusive scan of the 0/1 flags)
+__global__ void active_list_kernel(const uint8_t *__restrict__ active, const int *__restrict__ act_off, int64_t N,
+                                   int *__restrict__ list) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N && active[n]) list[act_off[n]] = (int)n;
 }
 
 __global__ void meta_kernel(const int *task_in, const int *task_out, const int *slot_in, const int *slot_out,
@@ -162,7 +169,7 @@ extern "C" int lgcn_graph_sizes_query(int64_t N, int64_t E, lgcn_graph_sizes *ou
                  "graph: N=%lld / E=%lld exceed the int32 internal range (shard the edge list)",
                  (long long)N, (long long)E);
     const size_t e1 = (size_t)(E > 0 ? E : 1);
-    const size_t max_slots = 2 * e1 / LGCN_ROW_SPLIT + 2;
+    const size_t max_slots = 2 * e1 / (E < LGCN_SMALL_GRAPH ? LGCN_ROW_SPLIT_SMALL : LGCN_ROW_SPLIT) + 2;
     out->ptr_bytes = sizeof(int32_t) * (size_t)(N + 1);
     out->nbr_bytes = sizeof(int32_t) * e1;
     out->dis_bytes = sizeof(float) * (size_t)(N > 0 ? N : 1);
@@ -171,6 +178,7 @@ extern "C" int lgcn_graph_sizes_query(int64_t N, int64_t E, lgcn_graph_sizes *ou
     out->partial_bytes = sizeof(float) * PARTIAL_STRIDE * max_slots;
     out->counter_bytes = sizeof(int32_t) * max_slots;
     out->workspace_bytes = carve(nullptr, N, E).total;
+    out->active_list_bytes = sizeof(int32_t) * (size_t)(N > 0 ? N : 1);
     return LGCN_OK;
 }
 
@@ -187,12 +195,13 @@ extern "C" int lgcn_graph_build(const int64_t *edge_index, int64_t E, int64_t N,
     LGCN_REQUIRE(workspace_bytes >= sz.workspace_bytes, LGCN_E_WORKSPACE, "graph_build: workspace %zu < %zu",
                  workspace_bytes, sz.workspace_bytes);
     LGCN_REQUIRE(g->in_ptr && g->in_nbr && g->in_trip && g->out_ptr && g->out_nbr && g->out_trip && g->dis &&
-                 g->active && g->in_tasks && g->out_tasks && g->partials && g->slot_counters,
+                 g->active && g->in_tasks && g->out_tasks && g->partials && g->slot_counters && g->active_list,
                  LGCN_E_INVALID, "graph_build: graph arrays not allocated");
     BuildWs w = carve(workspace, N, E);
     const int T = 256;
     const int gE = cdiv(E > 0 ? E : 1, T), gN = cdiv(N + 1, T);
     const int bits = bits_for(N);
+    const int split = E < LGCN_SMALL_GRAPH ? LGCN_ROW_SPLIT_SMALL : LGCN_ROW_SPLIT;
     int *in_ptr = (int *)g->in_ptr, *out_ptr = (int *)g->out_ptr;
 
     LGCN_CUDA(cudaMemsetAsync(w.meta, 0, sizeof(long long) * META_COUNT, st));
@@ -227,17 +236,19 @@ extern "C" int lgcn_graph_build(const int64_t *edge_index, int64_t E, int64_t N,
         LGCN_CUDA(cudaMemsetAsync(in_ptr, 0, sz.ptr_bytes, st));
         LGCN_CUDA(cudaMemsetAsync(out_ptr, 0, sz.ptr_bytes, st));
     }
-    node_kernel<<<gN, T, 0, st>>>(in_ptr, out_ptr, N, (float *)g->dis, (uint8_t *)g->active, w.cnt_in, w.slot_in,
-                                  w.cnt_out, w.slot_out, w.act32);
+    node_kernel<<<gN, T, 0, st>>>(in_ptr, out_ptr, N, split, (float *)g->dis, (uint8_t *)g->active, w.cnt_in,
+                                  w.slot_in, w.cnt_out, w.slot_out, w.act32);
     LGCN_LAUNCH_CHECK();
     int *scans[5] = {w.cnt_in, w.slot_in, w.cnt_out, w.slot_out, w.act32};
     for (int i = 0; i < 5; ++i) {
         size_t tb = w.cub_bytes;
         LGCN_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, scans[i], scans[i], (int)(N + 1), st));
     }
-    task_kernel<<<gN, T, 0, st>>>(in_ptr, w.cnt_in, w.slot_in, N, (lgcn_task *)g->in_tasks);
+    task_kernel<<<gN, T, 0, st>>>(in_ptr, w.cnt_in, w.slot_in, N, split, (lgcn_task *)g->in_tasks);
     LGCN_LAUNCH_CHECK();
-    task_kernel<<<gN, T, 0, st>>>(out_ptr, w.cnt_out, w.slot_out, N, (lgcn_task *)g->out_tasks);
+    task_kernel<<<gN, T, 0, st>>>(out_ptr, w.cnt_out, w.slot_out, N, split, (lgcn_task *)g->out_tasks);
+    LGCN_LAUNCH_CHECK();
+    active_list_kernel<<<gN, T, 0, st>>>(g->active, w.act32, N, (int *)g->active_list);
     LGCN_LAUNCH_CHECK();
     meta_kernel<<<1, 1, 0, st>>>(w.cnt_in, w.cnt_out, w.slot_in, w.slot_out, w.act32, N, (int)U, w.meta);
     LGCN_LAUNCH_CHECK();
@@ -258,6 +269,6 @@ extern "C" int lgcn_graph_build(const int64_t *edge_index, int64_t E, int64_t N,
     g->n_in_slots = (int32_t)meta[META_IN_SLOTS];
     g->n_out_slots = (int32_t)meta[META_OUT_SLOTS];
     g->num_active = (int32_t)meta[META_ACTIVE];
-    g->pad = 0;
+    g->row_split = split;
     return LGCN_OK;
 }

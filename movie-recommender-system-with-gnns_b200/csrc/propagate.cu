@@ -245,10 +245,6 @@ prescale_kernel(Table e0, const float *__restrict__ dis, int row0, int n, float 
         reinterpret_cast<float4 *>(y0)[(size_t)row * D4 + l16] = f4scale(__ldg(dis + row), ldg4(e0.row4(row) + l16));
 }
 
-struct Range {              // tasks [tb,te) of the list and the node rows [rb,re) they cover
-    int tb, te, rb, re;
-};
-
 // One forward layer k of K over the tasks of `r`.  scaled_first: layer 1 reads e0 and applies dis[r]
 // per edge (single-GPU path); otherwise yin is the pre-scaled table y_{k-1} for every layer.
 int fwd_layer_impl(const lgcn_graph *g, const Table &e0, int k, int K, bool scaled_first, const float *yin,
@@ -256,7 +252,7 @@ int fwd_layer_impl(const lgcn_graph *g, const Table &e0, int k, int K, bool scal
                    float *rnorm, Range r, cudaStream_t st) {
     const float c0 = 1.0f / (float)((K + 1) * (K + 1));
     const bool first = k == 1 && scaled_first, last = k == K;
-    if (last && g->num_active < g->num_nodes && r.re > r.rb) {
+    if (last && r.inactive_rows && g->num_active < g->num_nodes && r.re > r.rb) {
         fwd_inactive_kernel<<<cdiv(r.re - r.rb, 2 * WARPS_PER_CTA), CTA_THREADS, 0, st>>>(
             e0, g->active, r.rb, r.re, c0, final_out, rnorm);
         LGCN_LAUNCH_CHECK();
@@ -284,7 +280,7 @@ int bwd_layer_impl(const lgcn_graph *g, const float *G, int j, int K, const floa
     const float c0 = 1.0f / (float)((K + 1) * (K + 1));
     const bool first = j == 1, last = j == K;
     double *ex0 = accum ? accum + 1 : nullptr, *ex1 = accum ? accum + 2 : nullptr;
-    if (last && g->num_active < g->num_nodes && r.re > r.rb) {
+    if (last && r.inactive_rows && g->num_active < g->num_nodes && r.re > r.rb) {
         bwd_inactive_kernel<<<cdiv(r.re - r.rb, 2 * WARPS_PER_CTA), CTA_THREADS, 0, st>>>(
             G, g->active, r.rb, r.re, c0, e0, neg_count, reg_coef, g->num_users, grad, ex0, ex1);
         LGCN_LAUNCH_CHECK();
@@ -316,7 +312,7 @@ int propagate_fwd_impl(const lgcn_graph *g, const float *user_w, const float *it
     const Table e0{user_w, item_w, g->num_users};
     float *y[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int k = 1; k < K; ++k) y[k] = work + (size_t)(k - 1) * n * D;
-    const Range all{0, g->n_in_tasks, 0, g->num_nodes};
+    const Range all{0, g->n_in_tasks, 0, g->num_nodes, true};
     for (int k = 1; k <= K; ++k) {
         int rc = fwd_layer_impl(g, e0, k, K, true, y[k - 1], k < K ? y[k] : nullptr, y[1], y[2], y[3], final_out,
                                 rnorm, all, st);
@@ -338,7 +334,7 @@ int propagate_bwd_impl(const lgcn_graph *g, const float *G, int K, const float *
                  "propagate_bwd: workspace %zu < %zu bytes", work_bytes, need);
     const Table e0{user_w, item_w, g->num_users};
     float *z[2] = {work, work ? work + n * D : nullptr};
-    const Range all{0, g->n_out_tasks, 0, g->num_nodes};
+    const Range all{0, g->n_out_tasks, 0, g->num_nodes, true};
     for (int j = 1; j <= K; ++j) {
         const float *zin = j == 1 ? nullptr : z[j & 1];          // written by layer j-1
         float *zout = j == K ? nullptr : z[(j - 1) & 1];
@@ -390,7 +386,7 @@ extern "C" int lgcn_fwd_layer(const lgcn_graph *g, const float *user_w, const fl
     LGCN_REQUIRE(task_begin >= 0 && task_end <= g->n_in_tasks && task_begin <= task_end, LGCN_E_INVALID,
                  "fwd_layer: task range [%d,%d) outside [0,%d)", task_begin, task_end, g->n_in_tasks);
     return fwd_layer_impl(g, Table{user_w, item_w, g->num_users}, k, num_layers, false, yin, yout, y1, y2, y3, final_out,
-                          rnorm, Range{task_begin, task_end, (int)row_begin, (int)row_end}, (cudaStream_t)stream);
+                          rnorm, Range{task_begin, task_end, (int)row_begin, (int)row_end, true}, (cudaStream_t)stream);
 }
 
 extern "C" int lgcn_bwd_layer(const lgcn_graph *g, const float *grad_final, int j, int num_layers, const float *zin,
@@ -406,6 +402,6 @@ extern "C" int lgcn_bwd_layer(const lgcn_graph *g, const float *grad_final, int 
     LGCN_REQUIRE(reg_coef == 0.f || (user_w && item_w && neg_count && accum), LGCN_E_INVALID,
                  "bwd_layer: regulariser needs weights, neg_count and accum");
     return bwd_layer_impl(g, grad_final, j, num_layers, zin, zout, Table{user_w, item_w, g->num_users}, neg_count,
-                          reg_coef, grad_e0, accum, Range{task_begin, task_end, (int)row_begin, (int)row_end},
+                          reg_coef, grad_e0, accum, Range{task_begin, task_end, (int)row_begin, (int)row_end, true},
                           (cudaStream_t)stream);
 }

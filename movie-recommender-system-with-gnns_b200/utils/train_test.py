@@ -25,6 +25,9 @@ from .helpers import get_triplets_indices, sample_negative
 # bpr_loss on gathered rows (drop-in signature)
 # ----------------------------------------------------------------------------------------------
 
+SPARSE_STEPS = True      # train(): use the touched-rows step for small batches (set False to force dense)
+
+
 class _BprRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, uf, u0, pf, p0, nf, n0, coeff):
@@ -88,16 +91,49 @@ class FusedAdam:
         self.exp_avg = torch.zeros(n, DIM, dtype=torch.float32, device=w.device)
         self.exp_avg_sq = torch.zeros(n, DIM, dtype=torch.float32, device=w.device)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=w.device)
+        self.row_step = torch.zeros(n, dtype=torch.int32, device=w.device)   # sparse steps: per-row progress
+        self.pending = False          # True while some rows still owe zero-gradient updates (sparse steps)
         self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
+        self._bc_table(1 << 16)
         self.buffers = StepBuffers(n, model.num_items, model.num_layers, w.device)
         self.losses = torch.zeros(1024, dtype=torch.float32, device=w.device)   # per-batch losses of an epoch
         self.c = CAdam()
         self._fill()
 
+    def _bc_table(self, length: int):
+        """(lr/(1-beta1^t), sqrt(1-beta2^t)) for t < length, in double like torch's _single_tensor_adam,
+        cast once to fp32.  Extended on demand (host_steps tracks how far training may have got)."""
+        t = np.arange(length, dtype=np.float64)
+        with np.errstate(divide="ignore"):
+            ss = self.lr / (1.0 - np.power(self.betas[0], t))
+        bc2 = np.sqrt(1.0 - np.power(self.betas[1], t))
+        tab = np.stack([ss, bc2], axis=1).astype(np.float32)
+        tab[0] = 0.0
+        self.bc_table = torch.from_numpy(tab).to(self.exp_avg.device).contiguous()
+        self.host_steps = getattr(self, "host_steps", 0)
+
     def _fill(self):
         c = self.c
         c.lr, c.beta1, c.beta2, c.eps, c.max_norm = self.lr, self.betas[0], self.betas[1], self.eps, self.max_norm
         c.step, c.m, c.v = self.step_count.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        c.bc_table, c.bc_len = self.bc_table.data_ptr(), self.bc_table.shape[0]
+        c.row_step = self.row_step.data_ptr()
+
+    def _count_step(self):
+        self.host_steps += 1
+        if self.host_steps + 2 >= self.bc_table.shape[0]:
+            self._bc_table(2 * self.bc_table.shape[0])
+            self._fill()
+
+    def flush(self):
+        """Replay the zero-gradient updates that sparse steps deferred, so that every row of the
+        weights / moments is at the current step (called before anything else reads the weights)."""
+        if self.pending:
+            m = self.model
+            check(lib().lgcn_adam_flush(byref(self.c), m.user_embedding.weight.data_ptr(),
+                                        m.item_embedding.weight.data_ptr(), m.num_users, m.num_items,
+                                        stream_ptr(self.exp_avg.device)))
+            self.pending = False
 
     def zero_grad(self):
         pass
@@ -110,19 +146,28 @@ class FusedAdam:
         return self.losses[i:i + 1]
 
     def state_dict(self):
+        self.flush()
         return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,
                 "lr": self.lr, "betas": self.betas, "eps": self.eps, "max_norm": self.max_norm}
 
     def load_state_dict(self, sd):
         self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"]); self.step_count.copy_(sd["step"])
         self.lr, self.betas, self.eps, self.max_norm = sd["lr"], tuple(sd["betas"]), sd["eps"], sd["max_norm"]
+        self.host_steps = int(self.step_count)
+        self.row_step.fill_(self.host_steps)
+        self.pending = False
+        self._bc_table(max(1 << 16, 2 * self.host_steps + 4))
         self._fill()
 
 
 def train_step(model, optimizer: FusedAdam, edge_index: torch.Tensor, neg: Optional[torch.Tensor] = None,
-               loss_out: Optional[torch.Tensor] = None, bpr_coeff: float = 5e-3) -> torch.Tensor:
+               loss_out: Optional[torch.Tensor] = None, bpr_coeff: float = 5e-3, sparse: bool = False) -> torch.Tensor:
     """The loop body utils/train_test.py:88-96 for one batch as one C-ABI call.  ``neg`` defaults to
-    the reference's sampling (utils/helpers.py:79-80).  Returns a 0-dim DEVICE tensor (no sync)."""
+    the reference's sampling (utils/helpers.py:79-80).  Returns a 0-dim DEVICE tensor (no sync).
+
+    ``sparse=True`` runs ``lgcn_train_step_sparse``: same arithmetic, but only the rows the batch
+    touches are visited; the other rows' zero-gradient Adam updates stay pending until they are next
+    touched or ``optimizer.flush()`` is called (``train`` does that at the end of the epoch)."""
     g = model.graph(edge_index)
     dev = edge_index.device
     if g.num_triplets == 0:
@@ -138,6 +183,17 @@ def train_step(model, optimizer: FusedAdam, edge_index: torch.Tensor, neg: Optio
     if not (uw.is_contiguous() and iw.is_contiguous()):
         raise LgcnError("embedding weights must be contiguous")
     optimizer.buffers.ensure_triplets(g.num_triplets)
+    optimizer._count_step()
+    if sparse:
+        if not optimizer.pending:          # dense steps leave dL/dfinal / the histogram dirty
+            optimizer.buffers.grad_final.zero_()
+            optimizer.buffers.neg_count.zero_()
+        optimizer.pending = True
+        check(lib().lgcn_train_step_sparse(g.ref, uw.data_ptr(), iw.data_ptr(), model.num_layers,
+                                           neg.contiguous().data_ptr(), bpr_coeff, byref(optimizer.c),
+                                           optimizer.buffers.ref, loss_out.data_ptr(), stream_ptr(dev)))
+        return loss_out
+    optimizer.flush()
     check(lib().lgcn_train_step(g.ref, uw.data_ptr(), iw.data_ptr(), model.num_layers, neg.contiguous().data_ptr(),
                                 bpr_coeff, byref(optimizer.c), optimizer.buffers.ref, loss_out.data_ptr(),
                                 stream_ptr(dev)))
@@ -151,10 +207,16 @@ def train(model: torch.nn.Module, optimizer, train_loader, device: torch.device)
         weights = []
         for batch in train_loader:
             batch = batch.to(device)
-            if batch.edge_index.shape[1] == 0 or model.graph(batch.edge_index).num_triplets == 0:
+            if batch.edge_index.shape[1] == 0:
+                continue
+            g = model.graph(batch.edge_index)
+            if g.num_triplets == 0:
                 continue                      # the reference would produce NaN here (App. B #13)
-            train_step(model, optimizer, batch.edge_index, loss_out=optimizer.loss_slot(len(weights)))
+            # Cluster-GCN batches touch a small part of the table: visit only those rows
+            sparse = SPARSE_STEPS and 2 * (g.num_active + g.num_triplets) < g.num_nodes
+            train_step(model, optimizer, batch.edge_index, loss_out=optimizer.loss_slot(len(weights)), sparse=sparse)
             weights.append(batch.edge_index.shape[1])
+        optimizer.flush()
         if not weights:
             return float("nan")
         w = torch.tensor(weights, dtype=torch.float64)

@@ -315,3 +315,79 @@ def test_no_fallback_on_cpu_tensors():
         m(train)
     with pytest.raises(_lib.LgcnError):
         tt.bpr_loss(*[torch.zeros(4, 64)] * 6)
+
+
+# ---------------------------------------------------------------------------------------------
+# sparse (touched-rows) step: same arithmetic as the dense step, deferred zero-gradient updates
+# ---------------------------------------------------------------------------------------------
+
+def _cluster_like_batches(g, train, parts):
+    cl = synthetic.hash_partition(g.num_nodes, parts)
+    out = []
+    for p in range(parts):
+        m = (cl[train[0]] == p) & (cl[train[1]] == p)
+        b = train[:, m].contiguous()
+        if int((b[0] < g.num_users).sum()) > 0:
+            out.append(b)
+    return out
+
+
+@pytest.mark.parametrize("shape,parts,k", [("ml100k", 6, 3), ("ml1m", 12, 2)])
+def test_sparse_steps_equal_dense_steps_and_oracle(shape, parts, k):
+    g, train, _, u0, i0 = _case(shape)
+    batches = _cluster_like_batches(g, train, parts)
+    assert len(batches) >= parts - 1
+    epochs = 2
+    negs = [[_negs(b, g.num_users, g.num_items, 1000 * e + i) for i, b in enumerate(batches)] for e in range(epochs)]
+    dev_b = [b.to(DEV) for b in batches]
+    results = {}
+    for mode in ("dense", "sparse"):
+        m = _model(g.num_users, g.num_items, k, u0, i0)
+        opt = tt.FusedAdam(m)
+        losses = []
+        for e in range(epochs):
+            for b, n in zip(dev_b, negs[e]):
+                G = m.graph(b)
+                assert 2 * (G.num_active + G.num_triplets) < G.num_nodes          # genuinely sparse batches
+                losses.append(tt.train_step(m, opt, b, n.to(DEV), sparse=(mode == "sparse")).clone())
+            if mode == "sparse":
+                assert opt.pending
+                opt.flush()
+                assert int(opt.row_step.min()) == int(opt.step_count) == (e + 1) * len(batches)
+                # invariants the next sparse step relies on
+                assert float(opt.buffers.grad_final.abs().max()) == 0.0 and int(opt.buffers.neg_count.abs().max()) == 0
+        results[mode] = (torch.cat(losses).cpu(), m.user_embedding.weight.detach().cpu().clone(),
+                         m.item_embedding.weight.detach().cpu().clone(), opt.exp_avg.cpu().clone(), opt.exp_avg_sq.cpu().clone())
+    ld, ud, idn, md, vd = results["dense"]
+    ls, us, isp, ms, vs = results["sparse"]
+    # same kernels and the same replayed Adam arithmetic; only the float-atomic order of the negative
+    # gradients differs between runs
+    assert float((ld - ls).abs().max()) < 1e-6 * float(ld.abs().max())
+    assert max_abs(us, ud) < ADAM_STEP_ATOL and max_abs(isp, idn) < ADAM_STEP_ATOL
+    assert normwise(ms, md) < 1e-4 and normwise(vs, vd) < 1e-4
+    # and both follow the reference's trajectory
+    st = ref.TrainState(u0, i0, k)
+    want = [st.step(b, n) for e in range(epochs) for b, n in zip(batches, negs[e])]
+    assert max(abs(float(a) - w) / abs(w) for a, w in zip(ls, want)) < 1e-4
+    steps = epochs * len(batches)
+    assert max_abs(us, st.user_w.detach()) < steps * ADAM_STEP_ATOL and max_abs(isp, st.item_w.detach()) < steps * ADAM_STEP_ATOL
+
+
+def test_train_epoch_uses_sparse_steps_and_flushes():
+    from lgcn_b200.data.dataset_handler import ClusterLoader, Data
+    g, train, k, u0, i0 = _case("ml100k")
+    parts = [Data(edge_index=b.to(DEV), num_nodes=g.num_nodes) for b in _cluster_like_batches(g, train, 8)]
+    m = _model(g.num_users, g.num_items, k, u0, i0)
+    opt = tt.FusedAdam(m)
+    torch.manual_seed(0)
+    l1 = tt.train(m, opt, ClusterLoader(parts, shuffle=True), DEV)
+    l2 = tt.train(m, opt, ClusterLoader(parts, shuffle=True), DEV)
+    assert not opt.pending and int(opt.row_step.min()) == int(opt.step_count) == 2 * len(parts)
+    assert np.isfinite(l1) and l2 < l1 < 0.0                          # the loss goes down
+    # rows of nodes that were in no batch and never sampled still followed dense Adam (momentum = 0 => unmoved)
+    assert torch.isfinite(m.user_embedding.weight).all()
+
+
+def _negs(train, nu, ni, seed):          # noqa: F811  (redefinition keeps the helper next to its users)
+    gen = torch.Generator().manual_seed(seed)
+    return torch.randint(0, ni, (int((train[0] < nu).sum()),), generator=gen)
