@@ -230,16 +230,30 @@ def run_c2(args):
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * len(host_parts),
            "note": "batches uploaded from pinned host memory every step, CSR rebuilt for each upload"}
 
-    # ---- per-stage device times over one epoch (events on the launch stream) ---------------------
+    # ---- per-stage device times of the DENSE step over one epoch (events on the launch stream) ----
     stage_ms = stage_breakdown(model, opt, live, graphs_of(model, live), k, dev)
     peak, peak_src = measured_peak_gbs()
     adam_bytes = 7 * n * 256                                       # p,m,v,grad read + p,m,v written
     adam_ms = stage_ms["clip_adam"] / len(live)
-    roofline = {"kernel": "clip_adam_kernel", "bound": "hbm", "achieved": adam_bytes / (adam_ms * 1e-3) / 1e9,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
-                "algorithmic_bytes_per_launch": adam_bytes, "avg_launch_ms": adam_ms}
-    roofline["frac"] = roofline["achieved"] / peak
     spmm = full_graph_propagation(model, train.to(dev), k, dev, peak)
+    # roofline kernel = the propagation layer (SURVEY.md sec.8d defines B_layer for it): one launch = one
+    # layer over the train graph, duration = event time of the K-layer call / K
+    b_layer = 2 * n * 256 + 8 * train.shape[1] + 4 * (n + 1)
+    layer_ms = spmm["ms"] / k
+    roofline = {"kernel": "rowtask_kernel<FwdOp> (one propagation layer, full train graph)", "bound": "hbm",
+                "achieved": b_layer / (layer_ms * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "traffic": ncu_traffic("rowtask_fwd_layer"), "algorithmic_bytes_per_launch": b_layer,
+                "avg_launch_ms": layer_ms,
+                "note": "table (56.7 MB) is L2-resident, so the kernel is bound by L2 gather latency/throughput "
+                        "(gather-model GB/s in spmm_full_graph), not by the compulsory HBM bytes"}
+    roofline["frac"] = roofline["achieved"] / peak
+    roofline_adam = {"kernel": "clip_adam_kernel (dense step)", "bound": "hbm",
+                     "achieved": adam_bytes / (adam_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "traffic": ncu_traffic("clip_adam"), "algorithmic_bytes_per_launch": adam_bytes,
+                     "avg_launch_ms": adam_ms}
+    roofline_adam["frac"] = roofline_adam["achieved"] / peak
+    n_sparse = sum(1 for gr in graphs_of(model, live) if 2 * (gr.num_active + gr.num_triplets) < gr.num_nodes)
+    launches = args.steps * (n_sparse * launches_per_step(k, True) + (len(live) - n_sparse) * launches_per_step(k, False))
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -248,11 +262,14 @@ def run_c2(args):
                                   f"E_train={train.shape[1]} directed, {NUM_PARTS} METIS parts "
                                   f"({len(live)} non-empty, {edges_per_epoch} intra-cluster edges), K={k}, dim=64, "
                                   "fwd+BPR+bwd+clip+Adam per batch, step = 1 epoch",
-                      "l2": "per-step working set (weights, Adam state, grads, activations ~ 8 x 56.7 MB) exceeds the "
-                            "126 MB L2; no explicit flush",
-                      "parallelism": "1 GPU"},
-           "clocks": clk, "e2e": e2e, "gpu_launches": int(args.steps * len(live) * launches_per_step(k)),
-           "roofline": roofline, "stage_ms_per_epoch": stage_ms, "spmm_full_graph": spmm,
+                      "l2": "an epoch touches ~0.9 GB of distinct rows/state (100 batches x ~9 MB) plus 24 MB of CSR, "
+                            "more than the 126 MB L2; no explicit flush",
+                      "parallelism": "1 GPU",
+                      "step_kinds": f"{n_sparse} touched-rows (sparse) steps replayed as CUDA graphs + "
+                                    f"{len(live) - n_sparse} dense steps per epoch"},
+           "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+           "roofline": roofline, "roofline_adam": roofline_adam, "dense_stage_ms_per_epoch": stage_ms,
+           "spmm_full_graph": spmm,
            "setup_ms": {"cluster_extract": extract_ms, "graph_build_100_batches": build_ms},
            "final_epoch_loss": losses[-1]}
     if not args.no_cpu:
@@ -260,9 +277,20 @@ def run_c2(args):
     return out
 
 
-def launches_per_step(k: int) -> int:
+def launches_per_step(k: int, sparse: bool) -> int:
+    if sparse:   # step_begin, mark_negs, 2 replays, K fwd, BPR A+B, K bwd, neg_rows_grad, 2 adam_rows
+        return 1 + 1 + 2 + k + 2 + k + 1 + 2
     # step_begin + inactive-row fwd + K fwd layers + BPR pass A + pass B + inactive-row bwd + K bwd + clip_adam
     return 1 + 1 + k + 2 + 1 + k + 1
+
+
+def ncu_traffic(key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the last committed ncu --set full
+    capture (profiles/roofline_traffic.json), or None."""
+    p = os.path.join(REPO, "profiles", "roofline_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(key, {}).get("dram_bytes")
 
 
 def graphs_of(model, parts):

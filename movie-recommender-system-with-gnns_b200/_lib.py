@@ -230,6 +230,7 @@ class StepBuffers:
         self.neg_count = torch.zeros(num_items, dtype=torch.int32, device=device)
         self.accum = torch.zeros(4, dtype=torch.float64, device=device)
         self.trip_scratch = torch.empty(2, **f32)
+        self.generation = 0
         # sparse steps: per-item stamp / list of the distinct inactive negatives of the current step
         self.neg_flag = torch.zeros(num_items, dtype=torch.int32, device=device)
         self.neg_list = torch.zeros(num_items, dtype=torch.int32, device=device)
@@ -252,6 +253,7 @@ class StepBuffers:
         if self.trip_scratch.numel() < 2 * p:
             self.trip_scratch = torch.empty(2 * p, dtype=torch.float32, device=self.device)
             self._fill()
+            self.generation += 1          # captured CUDA graphs hold the old address
 
     @property
     def ref(self):

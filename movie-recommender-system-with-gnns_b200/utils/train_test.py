@@ -26,6 +26,7 @@ from .helpers import get_triplets_indices, sample_negative
 # ----------------------------------------------------------------------------------------------
 
 SPARSE_STEPS = True      # train(): use the touched-rows step for small batches (set False to force dense)
+CUDA_GRAPHS = True       # train(): replay each batch's step as one CUDA graph from its second epoch on
 
 
 class _BprRows(torch.autograd.Function):
@@ -93,10 +94,14 @@ class FusedAdam:
         self.step_count = torch.zeros(1, dtype=torch.int64, device=w.device)
         self.row_step = torch.zeros(n, dtype=torch.int32, device=w.device)   # sparse steps: per-row progress
         self.pending = False          # True while some rows still owe zero-gradient updates (sparse steps)
+        self.dirty = False            # True when a dense step left dL/dfinal / the negative histogram non-zero
+        self.graphs = {}              # id(Graph) -> (Graph, CUDAGraph | None, loss slot | None)
+        self.captured = 0
+        self.graph_generation = 0
         self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
-        self._bc_table(1 << 16)
+        self._bc_table(1 << 18)
         self.buffers = StepBuffers(n, model.num_items, model.num_layers, w.device)
-        self.losses = torch.zeros(1024, dtype=torch.float32, device=w.device)   # per-batch losses of an epoch
+        self.losses = torch.zeros(8192, dtype=torch.float32, device=w.device)   # per-batch losses (see train)
         self.c = CAdam()
         self._fill()
 
@@ -124,6 +129,8 @@ class FusedAdam:
         if self.host_steps + 2 >= self.bc_table.shape[0]:
             self._bc_table(2 * self.bc_table.shape[0])
             self._fill()
+            self.graphs.clear()           # captured launches hold the old table address
+            self.captured = 0
 
     def flush(self):
         """Replay the zero-gradient updates that sparse steps deferred, so that every row of the
@@ -138,12 +145,11 @@ class FusedAdam:
     def zero_grad(self):
         pass
 
-    def loss_slot(self, i: int) -> torch.Tensor:
-        if i >= self.losses.numel():
-            grown = torch.zeros(2 * self.losses.numel(), dtype=torch.float32, device=self.losses.device)
-            grown[: self.losses.numel()] = self.losses
-            self.losses = grown
-        return self.losses[i:i + 1]
+    def graph_ready(self, g, sparse: bool) -> bool:
+        """Capturing freezes buffer addresses: the scratch must already fit this batch, the bias
+        table must have room, and the zero-invariants of the sparse step must hold."""
+        return (self.buffers.trip_scratch.numel() >= 2 * g.num_triplets and not (sparse and self.dirty)
+                and self.host_steps + (1 << 12) < self.bc_table.shape[0])
 
     def state_dict(self):
         self.flush()
@@ -185,43 +191,97 @@ def train_step(model, optimizer: FusedAdam, edge_index: torch.Tensor, neg: Optio
     optimizer.buffers.ensure_triplets(g.num_triplets)
     optimizer._count_step()
     if sparse:
-        if not optimizer.pending:          # dense steps leave dL/dfinal / the histogram dirty
+        if optimizer.dirty:                # dense steps leave dL/dfinal / the histogram dirty
             optimizer.buffers.grad_final.zero_()
             optimizer.buffers.neg_count.zero_()
+            optimizer.dirty = False
         optimizer.pending = True
-        check(lib().lgcn_train_step_sparse(g.ref, uw.data_ptr(), iw.data_ptr(), model.num_layers,
-                                           neg.contiguous().data_ptr(), bpr_coeff, byref(optimizer.c),
-                                           optimizer.buffers.ref, loss_out.data_ptr(), stream_ptr(dev)))
-        return loss_out
-    optimizer.flush()
-    check(lib().lgcn_train_step(g.ref, uw.data_ptr(), iw.data_ptr(), model.num_layers, neg.contiguous().data_ptr(),
-                                bpr_coeff, byref(optimizer.c), optimizer.buffers.ref, loss_out.data_ptr(),
-                                stream_ptr(dev)))
+    else:
+        optimizer.flush()
+    _launch_step(model, optimizer, g, neg.contiguous(), loss_out, bpr_coeff, sparse)
     return loss_out
+
+
+def _launch_step(model, optimizer, g, neg, loss_out, bpr_coeff, sparse):
+    uw, iw = model.user_embedding.weight, model.item_embedding.weight
+    fn = lib().lgcn_train_step_sparse if sparse else lib().lgcn_train_step
+    if not sparse:
+        optimizer.dirty = True
+    check(fn(g.ref, uw.data_ptr(), iw.data_ptr(), model.num_layers, neg.data_ptr(), bpr_coeff, byref(optimizer.c),
+             optimizer.buffers.ref, loss_out.data_ptr(), stream_ptr(neg.device)))
+
+
+def _train_epoch_fused(model, optimizer: "FusedAdam", train_loader, device) -> float:
+    """One epoch on the fused path.  Per batch: one C-ABI call (sparse or dense step); from the second
+    time a batch tensor is seen its whole step -- negative sampling included -- is replayed as ONE
+    CUDA graph launch (the reference's loader hands back the same tensors every epoch,
+    data/dataset_handler.py:277-285).  The only host<->device sync is the loss read-back at the end."""
+    weights, slots = [], []
+    cap = optimizer.losses.numel() // 2          # [0,cap): this epoch's eager steps; [cap,2cap): captured graphs
+    if len(optimizer.graphs) > cap:              # fresh tensors every epoch: forget the never-captured ones
+        optimizer.graphs = {k: v for k, v in optimizer.graphs.items() if v[1] is not None}
+    for batch in train_loader:
+        batch = batch.to(device)
+        ei = batch.edge_index
+        if ei.shape[1] == 0:
+            continue
+        g = model.graph(ei)
+        if g.num_triplets == 0:
+            continue                      # the reference would produce NaN here (App. B #13)
+        if optimizer.buffers.generation != optimizer.graph_generation:
+            optimizer.graphs.clear()      # a scratch buffer moved: captured launches are stale
+            optimizer.graph_generation, optimizer.captured = optimizer.buffers.generation, 0
+        # Cluster-GCN batches touch a small part of the table: visit only those rows
+        sparse = SPARSE_STEPS and 2 * (g.num_active + g.num_triplets) < g.num_nodes
+        entry = optimizer.graphs.get(id(g)) if CUDA_GRAPHS else None
+        if entry is not None and entry[0] is not g:
+            entry = None
+        if entry is not None and entry[1] is not None:                      # replay
+            optimizer._count_step()
+            if sparse:
+                optimizer.pending = True
+            else:
+                optimizer.flush()
+                optimizer.dirty = True
+            entry[1].replay()
+            slot = entry[2]
+        elif (entry is not None and optimizer.graph_ready(g, sparse) and optimizer.captured < cap
+              and len(weights) < cap):                                      # second sighting: capture
+            slot = cap + optimizer.captured
+            optimizer.captured += 1
+            optimizer._count_step()
+            if not sparse:
+                optimizer.flush()
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                neg = torch.randint(0, model.num_items, (g.num_triplets,), device=device)
+                _launch_step(model, optimizer, g, neg, optimizer.losses[slot:slot + 1], 5e-3, sparse)
+            optimizer.graphs[id(g)] = (g, cg, slot)
+            if sparse:
+                optimizer.pending = True
+            cg.replay()
+        else:                                                               # first sighting: eager
+            slot = len(weights)
+            if slot >= cap:
+                raise LgcnError(f"more than {cap} batches in one epoch: enlarge FusedAdam.losses")
+            train_step(model, optimizer, ei, loss_out=optimizer.losses[slot:slot + 1], sparse=sparse)
+            if CUDA_GRAPHS and entry is None:
+                optimizer.graphs[id(g)] = (g, None, None)
+        weights.append(ei.shape[1])
+        slots.append(slot)
+    optimizer.flush()
+    if not weights:
+        return float("nan")
+    w = torch.tensor(weights, dtype=torch.float64)
+    losses = optimizer.losses[torch.tensor(slots, device=optimizer.losses.device)].double().cpu()   # the only sync
+    return float((losses * w).sum() / w.sum())
 
 
 def train(model: torch.nn.Module, optimizer, train_loader, device: torch.device) -> float:
     """One epoch (utils/train_test.py:66-103): edge-count-weighted mean of the batch losses."""
     model.train()
     if isinstance(optimizer, FusedAdam):
-        weights = []
-        for batch in train_loader:
-            batch = batch.to(device)
-            if batch.edge_index.shape[1] == 0:
-                continue
-            g = model.graph(batch.edge_index)
-            if g.num_triplets == 0:
-                continue                      # the reference would produce NaN here (App. B #13)
-            # Cluster-GCN batches touch a small part of the table: visit only those rows
-            sparse = SPARSE_STEPS and 2 * (g.num_active + g.num_triplets) < g.num_nodes
-            train_step(model, optimizer, batch.edge_index, loss_out=optimizer.loss_slot(len(weights)), sparse=sparse)
-            weights.append(batch.edge_index.shape[1])
-        optimizer.flush()
-        if not weights:
-            return float("nan")
-        w = torch.tensor(weights, dtype=torch.float64)
-        losses = optimizer.losses[: len(weights)].double().cpu()          # the epoch's only sync
-        return float((losses * w).sum() / w.sum())
+        return _train_epoch_fused(model, optimizer, train_loader, device)
 
     total_loss, total_w = 0.0, 0
     for batch in train_loader:
