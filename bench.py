@@ -252,7 +252,7 @@ def run_c2(args):
                      "traffic": ncu_traffic("clip_adam"), "algorithmic_bytes_per_launch": adam_bytes,
                      "avg_launch_ms": adam_ms}
     roofline_adam["frac"] = roofline_adam["achieved"] / peak
-    n_sparse = sum(1 for gr in graphs_of(model, live) if 2 * (gr.num_active + gr.num_triplets) < gr.num_nodes)
+    n_sparse = sum(1 for gr in graphs_of(model, live) if tt.sparse_step_pays(gr))
     launches = args.steps * (n_sparse * launches_per_step(k, True) + (len(live) - n_sparse) * launches_per_step(k, False))
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -363,6 +363,39 @@ def full_graph_propagation(model, train_dev, k, dev, peak):
     return {"edges": e, "layers": k, "ms": ms, "edges_per_s": e * k / (ms * 1e-3),
             "algorithmic_gbs": k * b_layer / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": k * b_layer / (ms * 1e-3) / 1e9 / peak,
             "gather_model_gbs": k * gather / (ms * 1e-3) / 1e9}
+
+
+# --------------------------------------------------------------------------------------------
+# C4: full-rank evaluation (reported inside the C2 line and on its own with --workload c4)
+# --------------------------------------------------------------------------------------------
+
+def run_c4(args, shape="ml25m"):
+    from lgcn_b200.utils import recommend as rec
+    dev = torch.device("cuda:0")
+    g = synthetic.make_graph(shape, seed=0)
+    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
+    ue, ie = u0.to(dev), i0.to(dev)
+    train, test = g.edges("train").to(dev), g.edges("test").to(dev)
+    ptr, idx = rec.exclusion_csr(train, g.num_users)
+    k = 20
+
+    def run():
+        return rec.score_topk(ue, ie, k, True, ptr, idx)
+    for _ in range(2):
+        run()
+    ts = []
+    for _ in range(max(3, min(args.steps, 10))):
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); run(); z.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(z))
+    ms = float(np.median(ts))
+    m = rec.full_rank_eval(ue, ie, train, test, g.num_users, k=k)
+    flop = 2.0 * g.num_users * g.num_items * 64
+    return {"workload": f"C4 full-rank eval {g.num_users} x {g.num_items} x 64, train-edge mask, top-{k}",
+            "ms": ms, "scores_per_s": g.num_users * g.num_items / (ms * 1e-3), "tflops_fp32": flop / (ms * 1e-3) / 1e12,
+            "math": "fp32 FFMA tiles (tensor-core path pending)", "recall@20": m["recall"], "ndcg@20": m["ndcg"],
+            "users_with_test_items": m["users"], "note": "random-init embeddings: recall/NDCG are chance level"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -537,8 +570,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3"])
+    ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3", "c4"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eval", action="store_true", help="skip the C4 full-rank evaluation section")
     args = ap.parse_args()
     if args.workload is None:
         args.workload = "c2" if args.gpus == 1 else "c3"
@@ -547,8 +581,12 @@ def main():
         if out is not None:
             print(json.dumps(out))
         return
-    if args.gpus == 1 and args.workload in ("c1", "c2"):
+    if args.workload == "c4":
+        out = run_c4(args)
+    elif args.gpus == 1 and args.workload in ("c1", "c2"):
         out = run_c2(args)
+        if args.workload == "c2" and not args.no_eval:
+            out["eval_full_rank_c4"] = run_c4(args)
     else:
         out = run_c3(args)
     if out is not None:

@@ -87,6 +87,7 @@ typedef struct lgcn_graph {
     int32_t num_active;              /* nodes with active[n] == 1                             */
     int32_t row_split;               /* max edges per task used for this graph                */
     const int32_t *active_list;      /* [num_active] ascending ids of the active nodes        */
+    int32_t *sched;                  /* [2] zero between launches: dynamic task scheduler state */
 } lgcn_graph;
 
 /* ---- K0: graph build ------------------------------------------------------------------ */

@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblgcn_b200.so")
+LIB_PATH = os.environ.get("LGCN_LIB_PATH") or os.path.join(_HERE, "csrc", "liblgcn_b200.so")   # env: tuning variants
 
 DIM = 64
 ROW_SPLIT = 512
@@ -50,6 +50,7 @@ class CGraph(Structure):
         ("n_in_slots", c_int32), ("n_out_slots", c_int32),
         ("partials", c_void_p), ("slot_counters", c_void_p),
         ("num_active", c_int32), ("row_split", c_int32), ("active_list", c_void_p),
+        ("sched", c_void_p),
     ]
 
 
@@ -198,6 +199,8 @@ class Graph:
         self.slot_counters = torch.zeros(nslots, **i32)
         self.active_list = self.active_list[: max(c.num_active, 1)].clone()
         c.active_list = self.active_list.data_ptr()
+        self.sched = torch.zeros(2, **i32)
+        c.sched = self.sched.data_ptr()
         c.in_tasks, c.out_tasks = self.in_tasks.data_ptr(), self.out_tasks.data_ptr()
         c.partials, c.slot_counters = self.partials.data_ptr(), self.slot_counters.data_ptr()
         self.c = c

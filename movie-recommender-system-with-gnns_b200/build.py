@@ -47,6 +47,27 @@ def _run(cmd, log):
         raise RuntimeError("build failed:\n" + "\n".join(log[-1:]))
 
 
+def build_variant(tag: str, defines: dict) -> str:
+    """Tuning aid: a differently parameterised copy of the library, csrc/build/variants/liblgcn_<tag>.so
+    (select it with LGCN_LIB_PATH).  Not used by the product path."""
+    vdir = os.path.join(CSRC, "build", "variants", tag)
+    os.makedirs(vdir, exist_ok=True)
+    lib = os.path.join(CSRC, "build", "variants", f"liblgcn_{tag}.so")
+    flags = [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + [f"-D{k}={v}" for k, v in defines.items()]
+    log: list = []
+
+    def cc(name):
+        obj = os.path.join(vdir, name + ".o")
+        _run([NVCC, *flags, "-c", os.path.join(CSRC, name), "-o", obj], log)
+        return obj
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        objs = list(ex.map(cc, CU_SOURCES))
+    obj = os.path.join(vdir, "partition_metis.c.o")
+    _run(["gcc", "-O2", "-fPIC", "-I", INCLUDE, "-c", os.path.join(CSRC, "partition_metis.c"), "-o", obj], log)
+    _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs, obj, METIS_A, "-lcudart", "-lm"], log)
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     stamp = os.path.join(CSRC, "build", "digest.txt")
     dig = _digest()

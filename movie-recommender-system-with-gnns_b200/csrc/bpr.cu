@@ -250,14 +250,14 @@ int bpr_impl(const lgcn_graph *g, const float *F, const float *rnorm, const int6
         LGCN_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)g->num_nodes * D, st));
         BprUserOp<true> a{accum, nullptr, g->out_nbr, g->out_trip, neg, F, rnorm, g->num_users, invP, G,
                           neg_count, scratch, nullptr, Table{}, 0.f};
-        LGCN_CUDA(launch_rowtasks(a, g->out_tasks, utb, ute, g->partials, g->slot_counters, st));
+        LGCN_CUDA(launch_rowtasks(a, g->out_tasks, utb, ute, g->partials, g->slot_counters, g->sched, st));
         BprItemOp b{nullptr, nullptr, g->in_nbr, g->in_trip, F, rnorm, scratch, invP, G, urb, ure};
         LGCN_CUDA(launch_rowtasks(b, g->in_tasks, g->n_in_user_tasks, g->n_in_tasks, g->partials,
-                                  g->slot_counters, st));
+                                  g->slot_counters, g->sched, st));
     } else {
         BprUserOp<false> a{accum, nullptr, g->out_nbr, g->out_trip, neg, F, rnorm, g->num_users, invP,
                            nullptr, neg_count, nullptr, nullptr, Table{}, 0.f};
-        LGCN_CUDA(launch_rowtasks(a, g->out_tasks, utb, ute, g->partials, g->slot_counters, st));
+        LGCN_CUDA(launch_rowtasks(a, g->out_tasks, utb, ute, g->partials, g->slot_counters, g->sched, st));
     }
     return LGCN_OK;
 }
@@ -271,9 +271,9 @@ int bpr_sparse_impl(const lgcn_graph *g, const float *F, const float *rnorm, con
     const float c0 = 1.0f / (float)((K + 1) * (K + 1));
     BprUserOp<true, true> a{accum, nullptr, g->out_nbr, g->out_trip, neg, F, rnorm, g->num_users, invP, G,
                             neg_count, scratch, g->active, Table{user_w, item_w, g->num_users}, c0};
-    LGCN_CUDA(launch_rowtasks(a, g->out_tasks, 0, g->n_out_user_tasks, g->partials, g->slot_counters, st));
+    LGCN_CUDA(launch_rowtasks(a, g->out_tasks, 0, g->n_out_user_tasks, g->partials, g->slot_counters, g->sched, st));
     BprItemOp b{nullptr, nullptr, g->in_nbr, g->in_trip, F, rnorm, scratch, invP, G, 0, g->num_users};
-    LGCN_CUDA(launch_rowtasks(b, g->in_tasks, g->n_in_user_tasks, g->n_in_tasks, g->partials, g->slot_counters, st));
+    LGCN_CUDA(launch_rowtasks(b, g->in_tasks, g->n_in_user_tasks, g->n_in_tasks, g->partials, g->slot_counters, g->sched, st));
     return LGCN_OK;
 }
 

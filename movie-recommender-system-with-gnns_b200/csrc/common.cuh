@@ -9,7 +9,13 @@ namespace lgcn {
 
 constexpr int D = LGCN_DIM;                 // 64 fp32 = 256 B per embedding row
 constexpr int D4 = D / 4;                   // float4 per row (one per lane of a half-warp)
-constexpr int WARPS_PER_CTA = 8;
+#ifndef LGCN_WARPS
+#define LGCN_WARPS 8
+#endif
+#ifndef LGCN_UNROLL
+#define LGCN_UNROLL 8
+#endif
+constexpr int WARPS_PER_CTA = LGCN_WARPS;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 constexpr int PARTIAL_STRIDE = 80;          // floats per partial slot: 64 + scalar, 64 B aligned
 constexpr unsigned FULL = 0xffffffffu;

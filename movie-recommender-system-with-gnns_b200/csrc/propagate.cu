@@ -257,7 +257,7 @@ int fwd_layer_impl(const lgcn_graph *g, const Table &e0, int k, int K, bool scal
             e0, g->active, r.rb, r.re, c0, final_out, rnorm);
         LGCN_LAUNCH_CHECK();
     }
-    auto go = [&](auto op) { return launch_rowtasks(op, g->in_tasks, r.tb, r.te, g->partials, g->slot_counters, st); };
+    auto go = [&](auto op) { return launch_rowtasks(op, g->in_tasks, r.tb, r.te, g->partials, g->slot_counters, g->sched, st); };
     if (first && last)
         LGCN_CUDA(go(FwdOp<true, true>{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, nullptr, nullptr,
                                        {nullptr, nullptr, nullptr}, 0, c0, final_out, rnorm}));
@@ -285,7 +285,7 @@ int bwd_layer_impl(const lgcn_graph *g, const float *G, int j, int K, const floa
             G, g->active, r.rb, r.re, c0, e0, neg_count, reg_coef, g->num_users, grad, ex0, ex1);
         LGCN_LAUNCH_CHECK();
     }
-    auto go = [&](auto op) { return launch_rowtasks(op, g->out_tasks, r.tb, r.te, g->partials, g->slot_counters, st); };
+    auto go = [&](auto op) { return launch_rowtasks(op, g->out_tasks, r.tb, r.te, g->partials, g->slot_counters, g->sched, st); };
     if (first && last)
         LGCN_CUDA(go(BwdOp<true, true>{ex0, ex1, g->out_nbr, g->in_ptr, g->out_ptr, g->dis, G, zin, zout, c0, grad, e0,
                                        neg_count, reg_coef, g->num_users}));

@@ -95,7 +95,7 @@ extern "C" int lgcn_spmm(const lgcn_graph *g, const float *x, float *out, int tr
         LGCN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)g->num_nodes * D, st));
     SpmmOp op{nullptr, nullptr, transpose ? g->out_nbr : g->in_nbr, g->dis, x, out};
     LGCN_CUDA(launch_rowtasks(op, transpose ? g->out_tasks : g->in_tasks, 0, transpose ? g->n_out_tasks : g->n_in_tasks,
-                              g->partials, g->slot_counters, st));
+                              g->partials, g->slot_counters, g->sched, st));
     return LGCN_OK;
 }
 

@@ -211,6 +211,11 @@ def _launch_step(model, optimizer, g, neg, loss_out, bpr_coeff, sparse):
              optimizer.buffers.ref, loss_out.data_ptr(), stream_ptr(neg.device)))
 
 
+def sparse_step_pays(g) -> bool:
+    """Touched rows (nodes with edges + at most min(P, I) distinct negatives) under half the table."""
+    return SPARSE_STEPS and 2 * (g.num_active + min(g.num_triplets, g.num_items)) < g.num_nodes
+
+
 def _train_epoch_fused(model, optimizer: "FusedAdam", train_loader, device) -> float:
     """One epoch on the fused path.  Per batch: one C-ABI call (sparse or dense step); from the second
     time a batch tensor is seen its whole step -- negative sampling included -- is replayed as ONE
@@ -232,7 +237,7 @@ def _train_epoch_fused(model, optimizer: "FusedAdam", train_loader, device) -> f
             optimizer.graphs.clear()      # a scratch buffer moved: captured launches are stale
             optimizer.graph_generation, optimizer.captured = optimizer.buffers.generation, 0
         # Cluster-GCN batches touch a small part of the table: visit only those rows
-        sparse = SPARSE_STEPS and 2 * (g.num_active + g.num_triplets) < g.num_nodes
+        sparse = sparse_step_pays(g)
         entry = optimizer.graphs.get(id(g)) if CUDA_GRAPHS else None
         if entry is not None and entry[0] is not g:
             entry = None
