@@ -421,6 +421,10 @@ def run_c3(args):
     ops = sharded.CudaOps(tr, g.num_users, g.num_items, k)
     u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
     trainer = sharded.ShardedTrainer(ops, u0.to(dev), i0.to(dev), sharded.Comm())
+    exchange = ("single GPU, no exchange" if world == 1 else
+                ("fused into the SpMM epilogue: " + ("NVLS multicast stores" if ops.multicast else "per-peer NVLink stores")
+                 + " into symmetric memory + barrier per layer") if ops.p2p else
+                f"NCCL all-gather between kernels (symmetric memory unavailable: {ops.p2p_error})")
     p = ops.num_triplets
     torch.manual_seed(0)                       # same Philox stream on every rank => identical negatives
 
@@ -499,7 +503,7 @@ def run_c3(args):
                                    f"E_train={e} directed, K={k}, dim=64, fwd+BPR+bwd+clip+Adam, node-range sharded "
                                    f"over {world} GPU(s) with all-gather per layer + all-reduce of dL/dfinal",
                        "l2": "tables + activations + CSR (> 1 GB) exceed the 126 MB L2; no explicit flush",
-                       "parallelism": f"node-range x{world}"},
+                       "parallelism": f"node-range x{world}", "exchange": exchange},
             "clocks": clk, "gpu_launches": int(args.steps * (2 + 2 + 2 * k + 2 + 2 * k + 2 + 1)),
             "e2e": {"value": e / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(train.numel() * 8), "d2h_bytes_per_step": 4,

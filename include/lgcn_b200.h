@@ -190,16 +190,29 @@ int lgcn_clip_adam(const lgcn_adam *opt, float *user_w, float *item_w, int64_t n
  * ([task_begin,task_end) of the row-sorted task list covering rows [row_begin,row_end)); the
  * caller exchanges the produced row slabs between layers (NCCL all-gather / all-reduce, see
  * lgcn_b200/sharded.py).  Layer 1 here reads the PRE-SCALED table y0 = dis (.) e0. */
+/* Fused compute + all-gather.  When `peers` is given (world > 1) the tables the kernels PRODUCE
+ * (y0 / yout / final_out / rnorm / zout) must live at the same offset of a symmetric-memory region on
+ * every rank: base[p] is rank p's mapping of that region in this process (peer access over NVLink),
+ * mc_base the NVLS multicast alias (or NULL).  Each produced row is then stored into every rank's copy
+ * from the SpMM epilogue itself -- one multimem store through the NVSwitch, or `world` peer stores --
+ * so the transfer overlaps the gather-sum row by row and no separate all-gather runs; the caller only
+ * places a cross-rank barrier between layers.  peers == NULL: plain local stores. */
+typedef struct lgcn_peers {
+    int32_t world, rank;
+    void *mc_base;
+    void *base[8];
+} lgcn_peers;
+
 int lgcn_prescale(const lgcn_graph *g, const float *user_w, const float *item_w, int64_t row_begin,
-                  int64_t row_end, float *y0, void *stream);
+                  int64_t row_end, float *y0, const lgcn_peers *peers, void *stream);
 int lgcn_fwd_layer(const lgcn_graph *g, const float *user_w, const float *item_w, int k, int num_layers,
                    const float *yin, float *yout, const float *y1, const float *y2, const float *y3,
                    float *final_out, float *rnorm, int task_begin, int task_end, int64_t row_begin,
-                   int64_t row_end, void *stream);
+                   int64_t row_end, const lgcn_peers *peers, void *stream);
 int lgcn_bwd_layer(const lgcn_graph *g, const float *grad_final, int j, int num_layers, const float *zin,
                    float *zout, const float *user_w, const float *item_w, const int32_t *neg_count,
                    float reg_coef, float *grad_e0, double *accum, int task_begin, int task_end,
-                   int64_t row_begin, int64_t row_end, void *stream);
+                   int64_t row_begin, int64_t row_end, const lgcn_peers *peers, void *stream);
 /* lgcn_bpr_fwd_bwd restricted to the triplets of users [user_row_begin,user_row_end) (out-task range
  * [user_task_begin,user_task_end)); grad_final / neg_count are zeroed first so that the per-rank
  * results sum to the unsharded ones. */

@@ -65,6 +65,10 @@ class CAdam(Structure):
                 ("bc_table", c_void_p), ("bc_len", c_int64), ("row_step", c_void_p)]
 
 
+class CPeers(Structure):
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("mc_base", c_void_p), ("base", c_void_p * 8)]
+
+
 class CStepBuffers(Structure):
     _fields_ = [("final_emb", c_void_p), ("rnorm", c_void_p), ("grad_final", c_void_p), ("grad_e0", c_void_p),
                 ("work", c_void_p), ("work_bytes", c_size_t), ("neg_count", c_void_p),
@@ -110,11 +114,12 @@ def lib():
                                   c_void_p, c_void_p, c_void_p]
     L.lgcn_spmm.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int, c_void_p]
     L.lgcn_bpr_rows.argtypes = [c_void_p] * 6 + [c_int64, c_float, c_void_p, c_void_p, c_void_p] + [c_void_p] * 6 + [c_void_p]
-    L.lgcn_prescale.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]
+    L.lgcn_prescale.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(CPeers), c_void_p]
     L.lgcn_fwd_layer.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 7 + \
-        [c_int, c_int, c_int64, c_int64, c_void_p]
+        [c_int, c_int, c_int64, c_int64, POINTER(CPeers), c_void_p]
     L.lgcn_bwd_layer.argtypes = [POINTER(CGraph), c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p]
+                                 c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, POINTER(CPeers),
+                                 c_void_p]
     L.lgcn_bpr_fwd_bwd_range.argtypes = [POINTER(CGraph)] + [c_void_p] * 7 + [c_int, c_int, c_int64, c_int64, c_void_p]
     L.lgcn_clip_adam_rows.argtypes = [POINTER(CAdam), c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                       c_float, c_void_p, c_int64, c_int64, c_void_p]

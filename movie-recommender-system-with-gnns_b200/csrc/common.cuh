@@ -56,6 +56,59 @@ struct Table {
     }
 };
 
+// Fused compute + all-gather: where to store a produced row so that EVERY rank's copy of the table
+// receives it.  The tables live in symmetric memory (same offset on every rank), so a peer address is
+// the local address plus a per-peer delta; with NVLS a single store to the multicast alias is
+// replicated by the NVSwitch.  world <= 1: plain local store.
+struct Peers {
+    int world;
+    int use_mc;
+    long long mc_delta;          // multicast alias = local address + mc_delta
+    long long delta[8];          // peer p = local address + delta[p]   (delta[own rank] = 0)
+};
+
+static inline Peers local_only() {
+    Peers p{};
+    p.world = 1;
+    return p;
+}
+
+static inline Peers make_peers(const lgcn_peers *q) {
+    if (!q || q->world <= 1) return local_only();
+    Peers p{};
+    p.world = q->world;
+    const long long self = (long long)(uintptr_t)q->base[q->rank];
+    p.use_mc = q->mc_base != nullptr;
+    p.mc_delta = p.use_mc ? (long long)(uintptr_t)q->mc_base - self : 0;
+    for (int i = 0; i < q->world && i < 8; ++i) p.delta[i] = (long long)(uintptr_t)q->base[i] - self;
+    return p;
+}
+
+__device__ __forceinline__ void push4(float4 *local, const float4 &v, const Peers &P) {
+    if (P.world <= 1) { *local = v; return; }
+    if (P.use_mc) {
+        float4 *mc = reinterpret_cast<float4 *>(reinterpret_cast<char *>(local) + P.mc_delta);
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                     :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < P.world) *reinterpret_cast<float4 *>(reinterpret_cast<char *>(local) + P.delta[i]) = v;
+}
+
+__device__ __forceinline__ void push1(float *local, float v, const Peers &P) {
+    if (P.world <= 1) { *local = v; return; }
+    if (P.use_mc) {
+        float *mc = reinterpret_cast<float *>(reinterpret_cast<char *>(local) + P.mc_delta);
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(mc), "f"(v) : "memory");
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < P.world) *reinterpret_cast<float *>(reinterpret_cast<char *>(local) + P.delta[i]) = v;
+}
+
 // tasks [tb,te) of a row-sorted task list and the node rows [rb,re) they cover; inactive_rows: also
 // produce the rows without any incident edge (dense semantics) -- false in the sparse step.
 struct Range {

@@ -96,6 +96,7 @@ struct FwdOp {
     float c0;                // 1/(K+1)^2
     float *final_out;
     float *rnorm;
+    Peers peers;             // where produced rows go (all ranks' copies in the sharded path)
 
     __device__ __forceinline__ void accumulate(int, int begin, int end, int lane, float4 &acc, float &, float &, float &) const {
         if constexpr (kFirst) GatherScaled<true>{nbr, dis, e0, nullptr}.run(begin, end, lane, acc);
@@ -106,7 +107,7 @@ struct FwdOp {
         const int deg = __ldg(ptr + row + 1) - __ldg(ptr + row);
         if constexpr (!kLast) {
             const float inv = deg > 0 ? 1.0f / (float)deg : 0.f;
-            if (lane < 16) reinterpret_cast<float4 *>(yout)[(size_t)row * D4 + l16] = f4scale(inv, raw);
+            if (lane < 16) push4(reinterpret_cast<float4 *>(yout) + (size_t)row * D4 + l16, f4scale(inv, raw), peers);
         } else {
             float4 s = f4zero();
 #pragma unroll
@@ -118,10 +119,10 @@ struct FwdOp {
             f4fma(f, sq, s);
             f4fma(f, d, raw);
             f = f4scale(c0, f);
-            if (lane < 16) reinterpret_cast<float4 *>(final_out)[(size_t)row * D4 + l16] = f;
+            if (lane < 16) push4(reinterpret_cast<float4 *>(final_out) + (size_t)row * D4 + l16, f, peers);
             if (rnorm) {
                 const float n2 = half_sum(f4dot(f, f));
-                if (lane == 0) rnorm[row] = 1.0f / sqrtf(n2);
+                if (lane == 0) push1(rnorm + row, 1.0f / sqrtf(n2), peers);
             }
         }
     }
@@ -130,18 +131,18 @@ struct FwdOp {
 // Rows without any incident edge: final = e0 / (K+1)^2 (every propagated layer is zero).
 __global__ void __launch_bounds__(CTA_THREADS)
 fwd_inactive_kernel(Table e0, const uint8_t *__restrict__ active, int row0, int n, float c0,
-                    float *__restrict__ final_out, float *__restrict__ rnorm) {
+                    float *__restrict__ final_out, float *__restrict__ rnorm, Peers peers) {
     const int lane = threadIdx.x & 31, l16 = lane & 15;
     int row = row0 + (blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) * 2 + (lane >> 4);
     const bool ok = row < n && !active[row];
     float4 f = f4zero();
     if (ok) {
         f = f4scale(c0, ldg4(e0.row4(row) + l16));
-        reinterpret_cast<float4 *>(final_out)[(size_t)row * D4 + l16] = f;
+        push4(reinterpret_cast<float4 *>(final_out) + (size_t)row * D4 + l16, f, peers);
     }
     if (rnorm) {
         const float n2 = half_sum(f4dot(f, f));
-        if (ok && l16 == 0) rnorm[row] = 1.0f / sqrtf(n2);
+        if (ok && l16 == 0) push1(rnorm + row, 1.0f / sqrtf(n2), peers);
     }
 }
 
@@ -165,6 +166,7 @@ struct BwdOp {
     const int32_t *neg_count;
     float reg_coef;
     int num_users;
+    Peers peers;
 
     __device__ __forceinline__ void accumulate(int, int begin, int end, int lane, float4 &acc, float &, float &, float &) const {
         if constexpr (kFirst) GatherScaled<false>{nbr, dis, Table{}, G}.run(begin, end, lane, acc);
@@ -176,7 +178,7 @@ struct BwdOp {
         float4 h = ldg4(reinterpret_cast<const float4 *>(G) + (size_t)row * D4 + l16);
         f4fma(h, d, S);
         if constexpr (!kLast) {
-            if (lane < 16) reinterpret_cast<float4 *>(zout)[(size_t)row * D4 + l16] = f4scale(d, h);
+            if (lane < 16) push4(reinterpret_cast<float4 *>(zout) + (size_t)row * D4 + l16, f4scale(d, h), peers);
         } else {
             float4 g = f4scale(c0, h);
             if (reg_coef != 0.f) {
@@ -238,45 +240,45 @@ bwd_inactive_kernel(const float *__restrict__ G, const uint8_t *__restrict__ act
 // y0[r] = dis[r] * e0[r] for rows [row_begin,row_end): lets layer 1 run as a pure gather-sum when the
 // table is assembled from per-rank slabs (sharded path).
 __global__ void __launch_bounds__(CTA_THREADS)
-prescale_kernel(Table e0, const float *__restrict__ dis, int row0, int n, float *__restrict__ y0) {
+prescale_kernel(Table e0, const float *__restrict__ dis, int row0, int n, float *__restrict__ y0, Peers peers) {
     const int lane = threadIdx.x & 31, l16 = lane & 15;
     const int row = row0 + (blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) * 2 + (lane >> 4);
     if (row < n)
-        reinterpret_cast<float4 *>(y0)[(size_t)row * D4 + l16] = f4scale(__ldg(dis + row), ldg4(e0.row4(row) + l16));
+        push4(reinterpret_cast<float4 *>(y0) + (size_t)row * D4 + l16, f4scale(__ldg(dis + row), ldg4(e0.row4(row) + l16)), peers);
 }
 
 // One forward layer k of K over the tasks of `r`.  scaled_first: layer 1 reads e0 and applies dis[r]
 // per edge (single-GPU path); otherwise yin is the pre-scaled table y_{k-1} for every layer.
 int fwd_layer_impl(const lgcn_graph *g, const Table &e0, int k, int K, bool scaled_first, const float *yin,
                    float *yout, const float *y1, const float *y2, const float *y3, float *final_out,
-                   float *rnorm, Range r, cudaStream_t st) {
+                   float *rnorm, Range r, cudaStream_t st, const Peers &peers) {
     const float c0 = 1.0f / (float)((K + 1) * (K + 1));
     const bool first = k == 1 && scaled_first, last = k == K;
     if (last && r.inactive_rows && g->num_active < g->num_nodes && r.re > r.rb) {
         fwd_inactive_kernel<<<cdiv(r.re - r.rb, 2 * WARPS_PER_CTA), CTA_THREADS, 0, st>>>(
-            e0, g->active, r.rb, r.re, c0, final_out, rnorm);
+            e0, g->active, r.rb, r.re, c0, final_out, rnorm, peers);
         LGCN_LAUNCH_CHECK();
     }
     auto go = [&](auto op) { return launch_rowtasks(op, g->in_tasks, r.tb, r.te, g->partials, g->slot_counters, g->sched, st); };
     if (first && last)
         LGCN_CUDA(go(FwdOp<true, true>{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, nullptr, nullptr,
-                                       {nullptr, nullptr, nullptr}, 0, c0, final_out, rnorm}));
+                                       {nullptr, nullptr, nullptr}, 0, c0, final_out, rnorm, peers}));
     else if (first)
         LGCN_CUDA(go(FwdOp<true, false>{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, nullptr, yout,
-                                        {nullptr, nullptr, nullptr}, 0, c0, nullptr, nullptr}));
+                                        {nullptr, nullptr, nullptr}, 0, c0, nullptr, nullptr, peers}));
     else if (!last)
         LGCN_CUDA(go(FwdOp<false, false>{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, yin, yout,
-                                         {nullptr, nullptr, nullptr}, 0, c0, nullptr, nullptr}));
+                                         {nullptr, nullptr, nullptr}, 0, c0, nullptr, nullptr, peers}));
     else
         LGCN_CUDA(go(FwdOp<false, true>{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, yin, nullptr,
-                                        {y1, y2, y3}, K - 1, c0, final_out, rnorm}));
+                                        {y1, y2, y3}, K - 1, c0, final_out, rnorm, peers}));
     return LGCN_OK;
 }
 
 // One backward (Horner) layer j of K over the tasks of `r`; layer 1 gathers dis (.) G itself.
 int bwd_layer_impl(const lgcn_graph *g, const float *G, int j, int K, const float *zin, float *zout,
                    const Table &e0, const int32_t *neg_count, float reg_coef, float *grad, double *accum,
-                   Range r, cudaStream_t st) {
+                   Range r, cudaStream_t st, const Peers &peers) {
     const float c0 = 1.0f / (float)((K + 1) * (K + 1));
     const bool first = j == 1, last = j == K;
     double *ex0 = accum ? accum + 1 : nullptr, *ex1 = accum ? accum + 2 : nullptr;
@@ -288,16 +290,16 @@ int bwd_layer_impl(const lgcn_graph *g, const float *G, int j, int K, const floa
     auto go = [&](auto op) { return launch_rowtasks(op, g->out_tasks, r.tb, r.te, g->partials, g->slot_counters, g->sched, st); };
     if (first && last)
         LGCN_CUDA(go(BwdOp<true, true>{ex0, ex1, g->out_nbr, g->in_ptr, g->out_ptr, g->dis, G, zin, zout, c0, grad, e0,
-                                       neg_count, reg_coef, g->num_users}));
+                                       neg_count, reg_coef, g->num_users, peers}));
     else if (first)
         LGCN_CUDA(go(BwdOp<true, false>{nullptr, nullptr, g->out_nbr, g->in_ptr, g->out_ptr, g->dis, G, zin, zout, c0,
-                                        grad, e0, neg_count, reg_coef, g->num_users}));
+                                        grad, e0, neg_count, reg_coef, g->num_users, peers}));
     else if (!last)
         LGCN_CUDA(go(BwdOp<false, false>{nullptr, nullptr, g->out_nbr, g->in_ptr, g->out_ptr, g->dis, G, zin, zout, c0,
-                                         grad, e0, neg_count, reg_coef, g->num_users}));
+                                         grad, e0, neg_count, reg_coef, g->num_users, peers}));
     else
         LGCN_CUDA(go(BwdOp<false, true>{ex0, ex1, g->out_nbr, g->in_ptr, g->out_ptr, g->dis, G, zin, zout, c0, grad, e0,
-                                        neg_count, reg_coef, g->num_users}));
+                                        neg_count, reg_coef, g->num_users, peers}));
     return LGCN_OK;
 }
 
@@ -315,7 +317,7 @@ int propagate_fwd_impl(const lgcn_graph *g, const float *user_w, const float *it
     const Range all{0, g->n_in_tasks, 0, g->num_nodes, true};
     for (int k = 1; k <= K; ++k) {
         int rc = fwd_layer_impl(g, e0, k, K, true, y[k - 1], k < K ? y[k] : nullptr, y[1], y[2], y[3], final_out,
-                                rnorm, all, st);
+                                rnorm, all, st, local_only());
         if (rc) return rc;
     }
     return LGCN_OK;
@@ -338,7 +340,7 @@ int propagate_bwd_impl(const lgcn_graph *g, const float *G, int K, const float *
     for (int j = 1; j <= K; ++j) {
         const float *zin = j == 1 ? nullptr : z[j & 1];          // written by layer j-1
         float *zout = j == K ? nullptr : z[(j - 1) & 1];
-        int rc = bwd_layer_impl(g, G, j, K, zin, zout, e0, neg_count, reg_coef, grad, accum, all, st);
+        int rc = bwd_layer_impl(g, G, j, K, zin, zout, e0, neg_count, reg_coef, grad, accum, all, st, local_only());
         if (rc) return rc;
     }
     return LGCN_OK;
@@ -364,13 +366,13 @@ extern "C" int lgcn_propagate_bwd(const lgcn_graph *g, const float *grad_final, 
 // ---- sharded (owner-computes-by-row-range) entry points -------------------------------------------
 
 extern "C" int lgcn_prescale(const lgcn_graph *g, const float *user_w, const float *item_w, int64_t row_begin,
-                             int64_t row_end, float *y0, void *stream) {
+                             int64_t row_end, float *y0, const lgcn_peers *peers, void *stream) {
     using namespace lgcn;
     LGCN_REQUIRE(g && user_w && item_w && y0 && row_begin >= 0 && row_end <= g->num_nodes, LGCN_E_INVALID,
                  "prescale: bad argument");
     if (row_end <= row_begin) return LGCN_OK;
     prescale_kernel<<<cdiv(row_end - row_begin, 2 * WARPS_PER_CTA), CTA_THREADS, 0, (cudaStream_t)stream>>>(
-        Table{user_w, item_w, g->num_users}, g->dis, (int)row_begin, (int)row_end, y0);
+        Table{user_w, item_w, g->num_users}, g->dis, (int)row_begin, (int)row_end, y0, make_peers(peers));
     LGCN_LAUNCH_CHECK();
     return LGCN_OK;
 }
@@ -378,7 +380,7 @@ extern "C" int lgcn_prescale(const lgcn_graph *g, const float *user_w, const flo
 extern "C" int lgcn_fwd_layer(const lgcn_graph *g, const float *user_w, const float *item_w, int k, int num_layers,
                               const float *yin, float *yout, const float *y1, const float *y2, const float *y3,
                               float *final_out, float *rnorm, int task_begin, int task_end, int64_t row_begin,
-                              int64_t row_end, void *stream) {
+                              int64_t row_end, const lgcn_peers *peers, void *stream) {
     using namespace lgcn;
     LGCN_REQUIRE(g && user_w && item_w && yin && k >= 1 && k <= num_layers && num_layers <= 4, LGCN_E_INVALID,
                  "fwd_layer: bad argument");
@@ -386,13 +388,14 @@ extern "C" int lgcn_fwd_layer(const lgcn_graph *g, const float *user_w, const fl
     LGCN_REQUIRE(task_begin >= 0 && task_end <= g->n_in_tasks && task_begin <= task_end, LGCN_E_INVALID,
                  "fwd_layer: task range [%d,%d) outside [0,%d)", task_begin, task_end, g->n_in_tasks);
     return fwd_layer_impl(g, Table{user_w, item_w, g->num_users}, k, num_layers, false, yin, yout, y1, y2, y3, final_out,
-                          rnorm, Range{task_begin, task_end, (int)row_begin, (int)row_end, true}, (cudaStream_t)stream);
+                          rnorm, Range{task_begin, task_end, (int)row_begin, (int)row_end, true}, (cudaStream_t)stream,
+                          make_peers(peers));
 }
 
 extern "C" int lgcn_bwd_layer(const lgcn_graph *g, const float *grad_final, int j, int num_layers, const float *zin,
                               float *zout, const float *user_w, const float *item_w, const int32_t *neg_count,
                               float reg_coef, float *grad_e0, double *accum, int task_begin, int task_end,
-                              int64_t row_begin, int64_t row_end, void *stream) {
+                              int64_t row_begin, int64_t row_end, const lgcn_peers *peers, void *stream) {
     using namespace lgcn;
     LGCN_REQUIRE(g && grad_final && j >= 1 && j <= num_layers && num_layers <= 4, LGCN_E_INVALID, "bwd_layer: bad argument");
     LGCN_REQUIRE(j == 1 || zin, LGCN_E_INVALID, "bwd_layer: zin missing");
@@ -403,5 +406,5 @@ extern "C" int lgcn_bwd_layer(const lgcn_graph *g, const float *grad_final, int 
                  "bwd_layer: regulariser needs weights, neg_count and accum");
     return bwd_layer_impl(g, grad_final, j, num_layers, zin, zout, Table{user_w, item_w, g->num_users}, neg_count,
                           reg_coef, grad_e0, accum, Range{task_begin, task_end, (int)row_begin, (int)row_end, true},
-                          (cudaStream_t)stream);
+                          (cudaStream_t)stream, make_peers(peers));
 }

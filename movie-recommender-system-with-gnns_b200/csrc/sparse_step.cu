@@ -23,9 +23,9 @@
 namespace lgcn {
 
 int fwd_layer_impl(const lgcn_graph *, const Table &, int, int, bool, const float *, float *, const float *,
-                   const float *, const float *, float *, float *, Range, cudaStream_t);
+                   const float *, const float *, float *, float *, Range, cudaStream_t, const Peers &);
 int bwd_layer_impl(const lgcn_graph *, const float *, int, int, const float *, float *, const Table &,
-                   const int32_t *, float, float *, double *, Range, cudaStream_t);
+                   const int32_t *, float, float *, double *, Range, cudaStream_t, const Peers &);
 int bpr_sparse_impl(const lgcn_graph *, const float *, const float *, const int64_t *, float *, int32_t *, float *,
                     double *, const float *, const float *, int, cudaStream_t);
 __global__ void step_begin_kernel(int64_t *step, double *accum, int32_t *list_count);
@@ -200,7 +200,7 @@ extern "C" int lgcn_train_step_sparse(const lgcn_graph *g, float *user_w, float 
     int rc;
     for (int k = 1; k <= K; ++k)
         if ((rc = fwd_layer_impl(g, e0, k, K, true, y[k - 1], k < K ? y[k] : nullptr, y[1], y[2], y[3], buf->final_emb,
-                                 buf->rnorm, fin, st))) return rc;
+                                 buf->rnorm, fin, st, local_only()))) return rc;
     if ((rc = bpr_sparse_impl(g, buf->final_emb, buf->rnorm, neg, buf->grad_final, buf->neg_count, buf->trip_scratch,
                               buf->accum, user_w, item_w, K, st))) return rc;
     // backward over the active rows, then the inactive negatives
@@ -210,7 +210,7 @@ extern "C" int lgcn_train_step_sparse(const lgcn_graph *g, float *user_w, float 
     const Range fout{0, g->n_out_tasks, 0, g->num_nodes, false};
     for (int j = 1; j <= K; ++j)
         if ((rc = bwd_layer_impl(g, buf->grad_final, j, K, j == 1 ? nullptr : z[j & 1], j == K ? nullptr : z[(j - 1) & 1],
-                                 e0, buf->neg_count, reg_coef, buf->grad_e0, buf->accum, fout, st))) return rc;
+                                 e0, buf->neg_count, reg_coef, buf->grad_e0, buf->accum, fout, st, local_only()))) return rc;
     neg_rows_grad_kernel<<<grid_rows(max_negs), CTA_THREADS, 0, st>>>(buf->neg_list, buf->neg_list_count, g->num_users,
                                                                      buf->grad_final, c0, e0, buf->neg_count, reg_coef,
                                                                      buf->grad_e0, buf->accum + 1, buf->accum + 2);

@@ -20,6 +20,7 @@ injects a torch stand-in to check the sharded algorithm over gloo with world_siz
 """
 from __future__ import annotations
 
+import os
 from ctypes import byref
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
@@ -119,10 +120,17 @@ class Comm:
 # ----------------------------------------------------------------------------------------------
 
 class CudaOps:
-    """The product backend: each method is one C-ABI call on the rank's row / task ranges."""
+    """The product backend: each method is one C-ABI call on the rank's row / task ranges.
+
+    p2p=True (default when world > 1): the exchanged tables (y_k, z_j, final, rnorm) live in one
+    symmetric-memory region and the kernels store every produced row straight into all ranks' copies
+    (NVLS multicast store, or per-peer stores over NVLink) -- the all-gather is fused into the SpMM
+    epilogue and only a cross-rank barrier separates layers.  p2p=False: NCCL all-gathers between
+    kernels (also the fallback when symmetric memory cannot be set up)."""
 
     def __init__(self, edge_index: torch.Tensor, num_users: int, num_items: int, num_layers: int,
-                 lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0):
+                 lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0,
+                 p2p: Optional[bool] = None, group=None):
         from . import _lib
         self._lib = _lib
         self.L = _lib.lib()
@@ -131,10 +139,47 @@ class CudaOps:
         self.nu, self.ni, self.n, self.k = num_users, num_items, num_users + num_items, num_layers
         f32 = dict(dtype=torch.float32, device=self.dev)
         n = self.n
-        self.y = [torch.zeros(n, DIM, **f32) for _ in range(num_layers)]        # y_0 .. y_{K-1}
-        self.z = [torch.zeros(n, DIM, **f32) for _ in range(min(2, max(num_layers - 1, 0)))]
-        self.final = torch.zeros(n, DIM, **f32)
-        self.rnorm = torch.zeros(n, **f32)
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if p2p is None:
+            p2p = world > 1 and os.environ.get("LGCN_P2P", "1") != "0"
+        nz = min(2, max(num_layers - 1, 0))
+        total = (num_layers + nz + 1) * n * DIM + n
+        self.p2p, self.peers, self.hdl, self.p2p_error = False, None, None, None
+        flat = None
+        if p2p and world > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                flat = symm_mem.empty(total, dtype=torch.float32, device=self.dev)
+                self.hdl = symm_mem.rendezvous(flat, group if group is not None else dist.group.WORLD)
+                c = _lib.CPeers()
+                c.world, c.rank = self.hdl.world_size, self.hdl.rank
+                mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+                if os.environ.get("LGCN_P2P_MULTICAST", "1") == "0":
+                    mc = 0
+                c.mc_base = mc if mc else None
+                for i, ptr in enumerate(self.hdl.buffer_ptrs):
+                    c.base[i] = ptr
+                self.peers, self.p2p, self.multicast = c, True, bool(mc)
+            except Exception as exc:           # no fabric / VMM support: NCCL all-gathers instead
+                self.p2p_error, flat = f"{type(exc).__name__}: {exc}", None
+        if flat is None:
+            flat = torch.empty(total, **f32)
+        flat.zero_()
+        off = 0
+
+        def take(rows_by_cols):
+            nonlocal off
+            t = flat[off:off + rows_by_cols]
+            off += rows_by_cols
+            return t
+        self.y = [take(n * DIM).view(n, DIM) for _ in range(num_layers)]          # y_0 .. y_{K-1}
+        self.z = [take(n * DIM).view(n, DIM) for _ in range(nz)]
+        self.final = take(n * DIM).view(n, DIM)
+        self.rnorm = take(n)
+        self._flat = flat
+        if self.p2p:
+            torch.cuda.synchronize(self.dev)
+            self.peer_barrier()
         self.G = torch.zeros(n, DIM, **f32)
         self.grad = torch.zeros(n, DIM, **f32)
         self.neg_count = torch.zeros(num_items, dtype=torch.int32, device=self.dev)
@@ -169,12 +214,19 @@ class CudaOps:
     def _s(self):
         return self._lib.stream_ptr(self.dev)
 
+    def _p(self):
+        return byref(self.peers) if self.p2p else None
+
+    def peer_barrier(self):
+        """All ranks' rows of the table just produced have landed everywhere (stream-ordered)."""
+        self.hdl.barrier(channel=0)
+
     def step_begin(self):
         self._lib.check(self.L.lgcn_step_begin(byref(self.adam), self.accum.data_ptr(), self._s()))
 
     def prescale(self, rb, re):
         self._lib.check(self.L.lgcn_prescale(self.g.ref, self.uw.data_ptr(), self.iw.data_ptr(), rb, re,
-                                             self.y[0].data_ptr(), self._s()))
+                                             self.y[0].data_ptr(), self._p(), self._s()))
 
     def fwd_layer(self, k, rb, re):
         tb, te = self._tasks(self.in_rows, rb, re)
@@ -183,7 +235,8 @@ class CudaOps:
         self._lib.check(self.L.lgcn_fwd_layer(
             self.g.ref, self.uw.data_ptr(), self.iw.data_ptr(), k, self.k, self.y[k - 1].data_ptr(),
             None if last else self.y[k].data_ptr(), ys[0], ys[1], ys[2],
-            self.final.data_ptr() if last else None, self.rnorm.data_ptr() if last else None, tb, te, rb, re, self._s()))
+            self.final.data_ptr() if last else None, self.rnorm.data_ptr() if last else None, tb, te, rb, re,
+            self._p(), self._s()))
 
     def bpr(self, neg, urb, ure):
         tb, te = self._tasks(self.out_rows, urb, ure)
@@ -200,7 +253,7 @@ class CudaOps:
         self._lib.check(self.L.lgcn_bwd_layer(
             self.g.ref, self.G.data_ptr(), j, self.k, zin, zout, self.uw.data_ptr(), self.iw.data_ptr(),
             self.neg_count.data_ptr(), reg, self.grad.data_ptr() if last else None, self.accum.data_ptr(),
-            tb, te, rb, re, self._s()))
+            tb, te, rb, re, self._p(), self._s()))
 
     def zbuf(self, j):
         return self.z[(j - 1) & 1]
@@ -230,7 +283,12 @@ class ShardedTrainer:
         self.segs = self.plan.segments(self.comm.rank)
         self.k = ops.k
 
-    def _gather(self, buf: torch.Tensor) -> None:
+    def _gather(self, buf: torch.Tensor, produced_by_kernel: bool = True) -> None:
+        """Make every rank's copy of ``buf`` complete.  Tables produced by a p2p-enabled kernel are
+        already being written into all copies; only a barrier is needed."""
+        if produced_by_kernel and getattr(self.ops, "p2p", False):
+            self.ops.peer_barrier()
+            return
         self.comm.allgather_rows(buf, self.plan.user_ptr)
         self.comm.allgather_rows(buf, self.plan.item_ptr)
 
@@ -267,7 +325,7 @@ class ShardedTrainer:
         """Full, up-to-date tables on every rank (for state_dict / best_model.pth)."""
         nu = self.plan.num_users
         full = torch.cat([self.user_w, self.item_w])
-        self._gather(full)
+        self._gather(full, produced_by_kernel=False)
         return full[:nu].clone(), full[nu:].clone()
 
     def propagate_only(self) -> torch.Tensor:

@@ -68,7 +68,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out_dir, shape, k, steps):
+def _worker(rank, world, port, out_dir, shape, k, steps, p2p):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dev = torch.device(f"cuda:{rank}")
     torch.cuda.set_device(dev)
@@ -76,24 +76,28 @@ def _worker(rank, world, port, out_dir, shape, k, steps):
     g = synthetic.make_graph(shape, seed=0)
     train = g.edges("train")
     u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
-    ops = sharded.CudaOps(train.to(dev), g.num_users, g.num_items, k)
+    ops = sharded.CudaOps(train.to(dev), g.num_users, g.num_items, k, p2p=p2p)
     tr = sharded.ShardedTrainer(ops, u0.to(dev), i0.to(dev), sharded.Comm())
     losses = [float(tr.step(n.to(dev))) for n in _negs(ops.num_triplets, g.num_items, steps)]
     uw, iw = tr.gather_weights()
     fin = tr.propagate_only()
-    torch.save({"losses": losses, "uw": uw.cpu(), "iw": iw.cpu(), "final": fin.cpu()}, os.path.join(out_dir, f"r{rank}.pt"))
+    torch.save({"losses": losses, "uw": uw.cpu(), "iw": iw.cpu(), "final": fin.cpu(), "p2p": ops.p2p,
+                "multicast": getattr(ops, "multicast", False), "p2p_error": ops.p2p_error},
+               os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [True, False], ids=["fused-p2p", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_multi_gpu_sharded_step_matches_oracle(tmp_path, world):
+def test_multi_gpu_sharded_step_matches_oracle(tmp_path, world, p2p):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     shape, k, steps = "ml100k", 3, 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), shape, k, steps), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), shape, k, steps, p2p), nprocs=world, join=True)
     g, train, u0, i0, st, want = _oracle(shape, k, steps)
     res = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
+    print("p2p", res[0]["p2p"], "multicast", res[0]["multicast"], "error", res[0]["p2p_error"])
     for r in res:
         assert max(abs(a - b) / abs(b) for a, b in zip(r["losses"], want)) < 1e-4
         assert max_abs(r["uw"], st.user_w.detach()) < steps * ADAM_STEP_ATOL
