@@ -403,6 +403,7 @@ def run_c4(args, shape="ml25m"):
 # --------------------------------------------------------------------------------------------
 
 def run_c3(args):
+    os.environ["NCCL_DEBUG"] = os.environ.get("LGCN_NCCL_DEBUG", "WARN")      # keep NCCL's banner off stdout
     import torch.distributed as dist
     from lgcn_b200 import sharded
     rank = int(os.environ.get("RANK", "0"))
@@ -411,7 +412,17 @@ def run_c3(args):
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)                      # NCCL prints its version banner to stdout on first use
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     shape = os.environ.get("LGCN_BENCH_SHAPE", "ml25m")
     g = synthetic.make_graph(shape, seed=0)
     k = synthetic.SHAPES[shape][3]
@@ -428,11 +439,12 @@ def run_c3(args):
     p = ops.num_triplets
     torch.manual_seed(0)                       # same Philox stream on every rank => identical negatives
 
-    def step():
-        neg = torch.randint(0, g.num_items, (p,), device=dev)
-        return trainer.step(neg)
+    use_graph = os.environ.get("LGCN_SHARDED_GRAPH", "0") == "1"     # opt-in until validated at every N
 
-    for _ in range(args.warmup):
+    def step():
+        return trainer.step_sampled(g.num_items, use_graph=use_graph)
+
+    for _ in range(max(args.warmup, 5 if use_graph else 0)):      # 3 eager + capture + 1 replay
         step()
     torch.cuda.synchronize()
     clocks = ClockSampler(local)
@@ -474,10 +486,11 @@ def run_c3(args):
     torch.cuda.synchronize(); trainer.comm.barrier()
     a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
+    from lgcn_b200 import _lib
     for _ in range(e2e_steps):
         ei = host_ei.to(dev, non_blocking=True)
-        from lgcn_b200 import _lib
-        ops.g = _lib.Graph(ei, g.num_users, g.num_items)
+        fresh = _lib.Graph(ei, g.num_users, g.num_items)           # K0 on the uploaded edge list
+        del fresh                                                   # (same content: the trainer keeps its CSR)
         float(step().item())
     z.record()
     torch.cuda.synchronize()
@@ -503,7 +516,11 @@ def run_c3(args):
                                    f"E_train={e} directed, K={k}, dim=64, fwd+BPR+bwd+clip+Adam, node-range sharded "
                                    f"over {world} GPU(s) with all-gather per layer + all-reduce of dL/dfinal",
                        "l2": "tables + activations + CSR (> 1 GB) exceed the 126 MB L2; no explicit flush",
-                       "parallelism": f"node-range x{world}", "exchange": exchange},
+                       "parallelism": f"node-range x{world}", "exchange": exchange,
+                       "launch": ("one CUDA graph per step (sampling + kernels + barriers + NCCL)"
+                                  if getattr(trainer, "_graph", None) is not None else
+                                  "eager launches" + (f" (graph capture failed: {trainer._graph_error})"
+                                                      if getattr(trainer, "_graph_failed", False) else ""))},
             "clocks": clk, "gpu_launches": int(args.steps * (2 + 2 + 2 * k + 2 + 2 * k + 2 + 1)),
             "e2e": {"value": e / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(train.numel() * 8), "d2h_bytes_per_step": 4,

@@ -203,6 +203,11 @@ typedef struct lgcn_peers {
     void *base[8];
 } lgcn_peers;
 
+/* Barrier between the ranks of `peers` on `stream`: flags_local = this rank's int32[8] flag array
+ * inside the symmetric region (zero-initialised), epoch = private device int32 (zero-initialised).
+ * Orders the peer / multicast stores of the preceding kernels before the following ones. */
+int lgcn_peer_barrier(const lgcn_peers *peers, int32_t *flags_local, int32_t *epoch, void *stream);
+
 int lgcn_prescale(const lgcn_graph *g, const float *user_w, const float *item_w, int64_t row_begin,
                   int64_t row_end, float *y0, const lgcn_peers *peers, void *stream);
 int lgcn_fwd_layer(const lgcn_graph *g, const float *user_w, const float *item_w, int k, int num_layers,

@@ -28,6 +28,7 @@ EXPORTS = [
     "lgcn_cluster_extract_workspace_bytes", "lgcn_cluster_extract", "lgcn_score_topk",
     "lgcn_spmm", "lgcn_bpr_rows", "lgcn_prescale", "lgcn_fwd_layer", "lgcn_bwd_layer",
     "lgcn_bpr_fwd_bwd_range", "lgcn_clip_adam_rows", "lgcn_train_step_sparse", "lgcn_adam_flush",
+    "lgcn_peer_barrier",
 ]
 
 
@@ -123,6 +124,7 @@ def lib():
     L.lgcn_bpr_fwd_bwd_range.argtypes = [POINTER(CGraph)] + [c_void_p] * 7 + [c_int, c_int, c_int64, c_int64, c_void_p]
     L.lgcn_clip_adam_rows.argtypes = [POINTER(CAdam), c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                       c_float, c_void_p, c_int64, c_int64, c_void_p]
+    L.lgcn_peer_barrier.argtypes = [POINTER(CPeers), c_void_p, c_void_p, c_void_p]
     L.lgcn_train_step_sparse.argtypes = L.lgcn_train_step.argtypes
     L.lgcn_adam_flush.argtypes = [POINTER(CAdam), c_void_p, c_void_p, c_int64, c_int64, c_void_p]
     for name in EXPORTS:

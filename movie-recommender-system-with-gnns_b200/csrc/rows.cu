@@ -85,7 +85,47 @@ bpr_rows_kernel(const float4 *__restrict__ uf, const float4 *__restrict__ u0, co
     }
 }
 
+// Cross-rank barrier for the fused all-gather: every rank bumps its private epoch, publishes it into
+// slot [rank] of every rank's flag array (symmetric memory; release at system scope AFTER a system
+// fence, so the rows stored by the preceding kernels of this stream are visible first), then waits
+// until all slots of its own array have reached the epoch.  State lives on the device => the launch
+// can be replayed from a CUDA graph.  Each GPU runs its own instance; nothing waits on a co-resident
+// kernel of the same GPU.
+__global__ void peer_barrier_kernel(int *flags_local, int *epoch, Peers P, int rank) {
+    __shared__ int e_sh;
+    if (threadIdx.x == 0) {
+        const int e = epoch[0] + 1;
+        epoch[0] = e;
+        e_sh = e;
+        __threadfence_system();
+    }
+    __syncthreads();
+    const int e = e_sh;
+    if ((int)threadIdx.x < P.world) {
+        int *dst = reinterpret_cast<int *>(reinterpret_cast<char *>(flags_local + rank) + P.delta[threadIdx.x]);
+        asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(dst), "r"(e) : "memory");
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags_local + threadIdx.x) : "memory");
+        } while (v < e);
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
 }  // namespace lgcn
+
+extern "C" int lgcn_peer_barrier(const lgcn_peers *peers, int32_t *flags_local, int32_t *epoch, void *stream) {
+    using namespace lgcn;
+    LGCN_REQUIRE(peers && flags_local && epoch && peers->world >= 1 && peers->world <= 8, LGCN_E_INVALID,
+                 "peer_barrier: bad argument");
+    if (peers->world == 1) return LGCN_OK;
+    Peers P = make_peers(peers);
+    // the flag array must be addressed through the same symmetric region as the tables
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags_local, epoch, P, peers->rank);
+    LGCN_LAUNCH_CHECK();
+    return LGCN_OK;
+}
 
 extern "C" int lgcn_spmm(const lgcn_graph *g, const float *x, float *out, int transpose, void *stream) {
     using namespace lgcn;

@@ -143,7 +143,7 @@ class CudaOps:
         if p2p is None:
             p2p = world > 1 and os.environ.get("LGCN_P2P", "1") != "0"
         nz = min(2, max(num_layers - 1, 0))
-        total = (num_layers + nz + 1) * n * DIM + n
+        total = (num_layers + nz + 1) * n * DIM + n + 64          # + barrier flags (int32 view of the tail)
         self.p2p, self.peers, self.hdl, self.p2p_error = False, None, None, None
         flat = None
         if p2p and world > 1:
@@ -176,10 +176,13 @@ class CudaOps:
         self.z = [take(n * DIM).view(n, DIM) for _ in range(nz)]
         self.final = take(n * DIM).view(n, DIM)
         self.rnorm = take(n)
+        self.flags = take(64).view(torch.int32)                    # [0:8] = per-rank arrival epochs
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._flat = flat
         if self.p2p:
             torch.cuda.synchronize(self.dev)
-            self.peer_barrier()
+            self.hdl.barrier(channel=0)            # everyone has zeroed its region before the first flag lands
+            torch.cuda.synchronize(self.dev)
         self.G = torch.zeros(n, DIM, **f32)
         self.grad = torch.zeros(n, DIM, **f32)
         self.neg_count = torch.zeros(num_items, dtype=torch.int32, device=self.dev)
@@ -194,6 +197,33 @@ class CudaOps:
         self.adam = c
         self.in_rows = self.g.in_tasks.view(-1, 8)[: self.g.c.n_in_tasks, 0].cpu()
         self.out_rows = self.g.out_tasks.view(-1, 8)[: self.g.c.n_out_tasks, 0].cpu()
+        self.local = None            # set by bind_segments(): rank-local task lists (one launch per layer)
+
+    def bind_segments(self, segs) -> None:
+        """Task order is free, so the tasks of ALL row segments this rank owns are packed into one
+        contiguous device list per direction: a layer is then ONE launch per rank (not one per
+        segment), and the ranges are resolved once instead of per call."""
+        import copy
+        lib_ = self._lib
+        parts_in, parts_out, n_user_out = [], [], 0
+        for rb, re in segs:
+            tb, te = self._tasks(self.in_rows, rb, re)
+            parts_in.append(self.g.in_tasks.view(-1, 8)[tb:te])
+            tb, te = self._tasks(self.out_rows, rb, re)
+            parts_out.append(self.g.out_tasks.view(-1, 8)[tb:te])
+            if re <= self.nu:
+                n_user_out += te - tb
+        self.loc_in = torch.cat(parts_in).contiguous().view(-1)
+        self.loc_out = torch.cat(parts_out).contiguous().view(-1)
+        c = lib_.CGraph.from_buffer_copy(self.g.c)
+        c.in_tasks, c.out_tasks = self.loc_in.data_ptr(), self.loc_out.data_ptr()
+        c.n_in_tasks, c.n_out_tasks = self.loc_in.numel() // 8, self.loc_out.numel() // 8
+        c.n_out_user_tasks = n_user_out
+        self.sched2 = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        c.sched = self.sched2.data_ptr()
+        self.local = c
+        self.segs = list(segs)
+        self.all_active = self.g.num_active == self.n
 
     # -- graph facts the planner needs
     @property
@@ -219,7 +249,8 @@ class CudaOps:
 
     def peer_barrier(self):
         """All ranks' rows of the table just produced have landed everywhere (stream-ordered)."""
-        self.hdl.barrier(channel=0)
+        self._lib.check(self.L.lgcn_peer_barrier(byref(self.peers), self.flags.data_ptr(), self.epoch.data_ptr(),
+                                                 self._s()))
 
     def step_begin(self):
         self._lib.check(self.L.lgcn_step_begin(byref(self.adam), self.accum.data_ptr(), self._s()))
@@ -229,29 +260,52 @@ class CudaOps:
                                              self.y[0].data_ptr(), self._p(), self._s()))
 
     def fwd_layer(self, k, rb, re):
-        tb, te = self._tasks(self.in_rows, rb, re)
+        """Layer k over rows [rb,re); (rb,re) == (None,None): all of this rank's segments at once."""
+        if rb is None:
+            gref, tb, te, rb, re = byref(self.local), 0, self.local.n_in_tasks, 0, 0
+        else:
+            gref = self.g.ref
+            tb, te = self._tasks(self.in_rows, rb, re)
         last = k == self.k
         ys = [self.y[i].data_ptr() if i < self.k else None for i in (1, 2, 3)]
         self._lib.check(self.L.lgcn_fwd_layer(
-            self.g.ref, self.uw.data_ptr(), self.iw.data_ptr(), k, self.k, self.y[k - 1].data_ptr(),
+            gref, self.uw.data_ptr(), self.iw.data_ptr(), k, self.k, self.y[k - 1].data_ptr(),
             None if last else self.y[k].data_ptr(), ys[0], ys[1], ys[2],
             self.final.data_ptr() if last else None, self.rnorm.data_ptr() if last else None, tb, te, rb, re,
             self._p(), self._s()))
 
     def bpr(self, neg, urb, ure):
-        tb, te = self._tasks(self.out_rows, urb, ure)
+        if self.local is not None:       # user tasks are the prefix of the packed by-source list; the item pass
+            gref, tb, te = byref(self.bpr_graph()), 0, self.local.n_out_user_tasks     # walks the GLOBAL by-target list
+        else:
+            gref = self.g.ref
+            tb, te = self._tasks(self.out_rows, urb, ure)
         self._lib.check(self.L.lgcn_bpr_fwd_bwd_range(
-            self.g.ref, self.final.data_ptr(), self.rnorm.data_ptr(), neg.data_ptr(), self.G.data_ptr(),
+            gref, self.final.data_ptr(), self.rnorm.data_ptr(), neg.data_ptr(), self.G.data_ptr(),
             self.neg_count.data_ptr(), self.scratch.data_ptr(), self.accum.data_ptr(), tb, te, urb, ure, self._s()))
 
+    def bpr_graph(self):
+        """Packed by-source tasks (pass A: own users) + the global by-target tasks (pass B: all items,
+        filtered by user range)."""
+        if getattr(self, "_bpr_c", None) is None:
+            c = self._lib.CGraph.from_buffer_copy(self.g.c)
+            c.out_tasks, c.n_out_tasks, c.n_out_user_tasks = self.local.out_tasks, self.local.n_out_tasks, self.local.n_out_user_tasks
+            c.sched = self.local.sched
+            self._bpr_c = c
+        return self._bpr_c
+
     def bwd_layer(self, j, rb, re, bpr_coeff):
-        tb, te = self._tasks(self.out_rows, rb, re)
+        if rb is None:
+            gref, tb, te, rb, re = byref(self.local), 0, self.local.n_out_tasks, 0, 0
+        else:
+            gref = self.g.ref
+            tb, te = self._tasks(self.out_rows, rb, re)
         last = j == self.k
         zin = None if j == 1 else self.z[j & 1].data_ptr()
         zout = None if last else self.z[(j - 1) & 1].data_ptr()
         reg = 2.0 * bpr_coeff / (64.0 * self.g.num_triplets)
         self._lib.check(self.L.lgcn_bwd_layer(
-            self.g.ref, self.G.data_ptr(), j, self.k, zin, zout, self.uw.data_ptr(), self.iw.data_ptr(),
+            gref, self.G.data_ptr(), j, self.k, zin, zout, self.uw.data_ptr(), self.iw.data_ptr(),
             self.neg_count.data_ptr(), reg, self.grad.data_ptr() if last else None, self.accum.data_ptr(),
             tb, te, rb, re, self._p(), self._s()))
 
@@ -282,6 +336,12 @@ class ShardedTrainer:
         self.plan = plan if plan is not None else ShardPlan.build(ind, outd, ops.nu, self.comm.world)
         self.segs = self.plan.segments(self.comm.rank)
         self.k = ops.k
+        # one launch per layer when the backend can pack this rank's segments and no row is edge-less
+        self.packed = False
+        if hasattr(ops, "bind_segments"):
+            ops.bind_segments(self.segs)
+            self.packed = ops.all_active
+        self.layer_segs = [(None, None)] if self.packed else self.segs
 
     def _gather(self, buf: torch.Tensor, produced_by_kernel: bool = True) -> None:
         """Make every rank's copy of ``buf`` complete.  Tables produced by a p2p-enabled kernel are
@@ -301,18 +361,19 @@ class ShardedTrainer:
             o.prescale(rb, re)
         self._gather(o.y[0])
         for layer in range(1, k + 1):
-            for rb, re in self.segs:
+            for rb, re in self.layer_segs:
                 o.fwd_layer(layer, rb, re)
             if layer < k:
                 self._gather(o.y[layer])
         self._gather(o.final)
-        self._gather(o.rnorm)
+        if not getattr(o, "p2p", False):
+            self._gather(o.rnorm)             # (p2p: same kernel, same barrier as `final`)
         urb, ure = self.segs[0]
         o.bpr(neg, urb, ure)
         self.comm.allreduce(o.G)
         self.comm.allreduce(o.neg_count)
         for j in range(1, k + 1):
-            for rb, re in self.segs:
+            for rb, re in self.layer_segs:
                 o.bwd_layer(j, rb, re, self.bpr_coeff)
             if j < k:
                 self._gather(o.zbuf(j))
@@ -320,6 +381,34 @@ class ShardedTrainer:
         for rb, re in self.segs:
             o.clip_adam(rb, re, self.bpr_coeff)
         return o.loss
+
+    def step_sampled(self, num_items: Optional[int] = None, use_graph: bool = True) -> torch.Tensor:
+        """One step with the reference's negative sampling (uniform ``randint`` per triplet,
+        utils/helpers.py:79-80) done on the device.  All ranks must hold the same torch CUDA RNG state
+        (same ``torch.manual_seed``) so that they draw identical negatives.  From the 4th call on the
+        whole step -- sampling, kernels, barriers, NCCL all-reduces -- is replayed as ONE CUDA graph
+        launch per rank, which removes the ~25 host calls per step that dominate at 8 GPUs."""
+        ni = self.plan.num_items if num_items is None else num_items
+        p, dev = self.ops.num_triplets, self.user_w.device
+        self._calls = getattr(self, "_calls", 0) + 1
+        if not use_graph or not self.user_w.is_cuda or getattr(self, "_graph_failed", False):
+            return self.step(torch.randint(0, ni, (p,), device=dev))
+        if getattr(self, "_graph", None) is None:
+            if self._calls <= 3:                       # eager warm-up (NCCL channels, allocator)
+                return self.step(torch.randint(0, ni, (p,), device=dev))
+            try:
+                torch.cuda.synchronize(dev)
+                self.comm.barrier()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._graph_loss = self.step(torch.randint(0, ni, (p,), device=dev))
+                self._graph = g
+            except Exception as exc:                   # capture not supported for some op: stay eager
+                self._graph_failed, self._graph_error = True, f"{type(exc).__name__}: {exc}"
+                torch.cuda.synchronize(dev)
+                return self.step(torch.randint(0, ni, (p,), device=dev))
+        self._graph.replay()
+        return self._graph_loss
 
     def gather_weights(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """Full, up-to-date tables on every rank (for state_dict / best_model.pth)."""
@@ -335,7 +424,7 @@ class ShardedTrainer:
             o.prescale(rb, re)
         self._gather(o.y[0])
         for layer in range(1, k + 1):
-            for rb, re in self.segs:
+            for rb, re in self.layer_segs:
                 o.fwd_layer(layer, rb, re)
             if layer < k:
                 self._gather(o.y[layer])
