@@ -304,6 +304,18 @@ int lgcn_score_topk(const float *user_emb, const float *item_emb, int64_t num_it
                     const int32_t *excl_idx, int k, int32_t *topk_idx, float *topk_val,
                     void *stream);
 
+/* Same with an explicit kernel choice: LGCN_SCORE_TENSOR = tcgen05 TF32 MMA with a 3-term hi/lo
+ * operand split (fp32-level accuracy), accumulator in TMEM, k <= 64; LGCN_SCORE_FFMA = fp32 FFMA tiles,
+ * k <= 128; LGCN_SCORE_AUTO picks the tensor-core kernel whenever k allows. */
+#define LGCN_SCORE_AUTO 0
+#define LGCN_SCORE_FFMA 1
+#define LGCN_SCORE_TENSOR 2
+#define LGCN_SCORE_AUTO_USES_TENSOR 1      /* validated on B200 (tests/test_gpu_cluster_score.py) */
+int lgcn_score_topk_ex(const float *user_emb, const float *item_emb, int64_t num_items,
+                       int64_t u_begin, int64_t u_end, int normalize, const int64_t *excl_ptr,
+                       const int32_t *excl_idx, int k, int32_t *topk_idx, float *topk_val, int algo,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,7 +28,7 @@ EXPORTS = [
     "lgcn_cluster_extract_workspace_bytes", "lgcn_cluster_extract", "lgcn_score_topk",
     "lgcn_spmm", "lgcn_bpr_rows", "lgcn_prescale", "lgcn_fwd_layer", "lgcn_bwd_layer",
     "lgcn_bpr_fwd_bwd_range", "lgcn_clip_adam_rows", "lgcn_train_step_sparse", "lgcn_adam_flush",
-    "lgcn_peer_barrier",
+    "lgcn_peer_barrier", "lgcn_score_topk_ex",
 ]
 
 
@@ -113,6 +113,8 @@ def lib():
                                        c_size_t, c_void_p]
     L.lgcn_score_topk.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int,
                                   c_void_p, c_void_p, c_void_p]
+    L.lgcn_score_topk_ex.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int,
+                                     c_void_p, c_void_p, c_int, c_void_p]
     L.lgcn_spmm.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int, c_void_p]
     L.lgcn_bpr_rows.argtypes = [c_void_p] * 6 + [c_int64, c_float, c_void_p, c_void_p, c_void_p] + [c_void_p] * 6 + [c_void_p]
     L.lgcn_prescale.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(CPeers), c_void_p]

@@ -1,0 +1,302 @@
+// K5 on the 5th-generation tensor cores: user x item scoring as a tcgen05 TF32 GEMM with the
+// accumulator in TMEM, fused with train-edge masking and a per-user top-k, so that the score matrix
+// (9.6 G scores at ML-25M) never leaves the SM.
+//
+// Replaces (same contract as score_topk.cu, the FFMA version):
+//   utils/recommend.py:39-61      normalise rows, matmul, sort, skip excluded, first 10
+//   utils/train_test.py:191-197   torch.mm(user_normalized, items.t()) + topk(k)
+//
+// fp32 parity on TF32 tensor cores: every fp32 operand x is split as x = hi + lo with hi = x with
+// the 13 low mantissa bits cleared (exactly a TF32 number) and lo = x - hi (exact in fp32, <= 13
+// significant bits, of which the MMA keeps 11).  score = hi.hi + hi.lo + lo.hi accumulated in fp32
+// in TMEM; the dropped lo.lo term and the truncation of lo are O(2^-21) relative -- well inside the
+// 1e-5 budget (measured in tests/test_gpu_cluster_score.py).  Cost: 3 MMAs per K-step.
+//
+// CTA = 128 users (TMEM lanes) x all items, streamed as 64-item tiles:
+//   warps 0-3  epilogue: thread t owns user t: tcgen05.ld of its 64 scores, compare with the user's
+//              k-th best kept in a register, mask train items with a 64-bit mask built from a cursor
+//              into the user's sorted exclusion row, insert survivors into the user's sorted list
+//              (shared memory, column per user => conflict-free)
+//   warp  4    one elected thread issues 24 tcgen05.mma (8 K-steps x 3 split terms, M=128 N=64 K=8)
+//              per tile and commits to mbarriers
+//   warps 5-8  producers: gather 64 item rows, L2-normalise, split hi/lo, store in the UMMA K-major
+//              no-swizzle ("interleaved") core-matrix layout, fence.proxy.async, arrive
+// Two shared-memory stages for B and two TMEM accumulator stages (2 x 64 columns) decouple the roles.
+#include "common.cuh"
+#include <limits.h>
+#include <math_constants.h>
+
+namespace lgcn {
+namespace tc {
+
+constexpr int BM = 128, BN = 64, BK = 64;
+constexpr int GROUP_BYTES = 2048;                 // 8 rows x 256 B: 16 core matrices of 8 x 16 B
+constexpr int A_BYTES = (BM / 8) * GROUP_BYTES;   // 32 KB per split half
+constexpr int B_BYTES = (BN / 8) * GROUP_BYTES;   // 16 KB per split half
+constexpr int NUM_EPI = 128, NUM_PROD = 128;
+constexpr int THREADS = NUM_EPI + 32 + NUM_PROD;  // 288
+constexpr int TMEM_COLS = 128;                    // 2 accumulator stages x 64 fp32 columns
+constexpr int KMAX = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// K-major, no swizzle: start address, LBO = 128 B between the two 16-byte K chunks of one MMA,
+// SBO = 2048 B between 8-row groups; descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((128 >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((GROUP_BYTES >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// kind::tf32, D = F32, A/B = TF32 K-major, N = 64, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ float4 split_hi(const float4 &v) {
+    return make_float4(__uint_as_float(__float_as_uint(v.x) & 0xffffe000u), __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                       __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+}
+
+// 8 rows x 256 B per warp pass: lane = (row r8 = lane % 8, chunk quarter c4 = lane / 8); each lane
+// loads the 4 chunks c = cb*4 + c4 of its row, the 4 lanes of a row reduce the squared norm.
+__device__ __forceinline__ void load_rows8(const float *__restrict__ tab, int64_t row0, int64_t nrows, bool normalize,
+                                           unsigned char *hi_base, unsigned char *lo_base, int group, int lane) {
+    const int r8 = lane & 7, c4 = lane >> 3;
+    const int64_t row = row0 + group * 8 + r8;
+    float4 v[4];
+    float n2 = 0.f;
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+        v[cb] = row < nrows ? ldg4(reinterpret_cast<const float4 *>(tab) + row * D4 + cb * 4 + c4) : f4zero();
+        n2 += f4dot(v[cb], v[cb]);
+    }
+    n2 += __shfl_xor_sync(FULL, n2, 8);
+    n2 += __shfl_xor_sync(FULL, n2, 16);
+    const float inv = normalize ? 1.0f / sqrtf(n2) : 1.0f;
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+        float4 x = row < nrows ? f4scale(inv, v[cb]) : f4zero();
+        const float4 h = split_hi(x);
+        const float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        const int off = group * GROUP_BYTES + (cb * 4 + c4) * 128 + r8 * 16;
+        *reinterpret_cast<float4 *>(hi_base + off) = h;
+        *reinterpret_cast<float4 *>(lo_base + off) = l;
+    }
+}
+
+struct __align__(16) Smem {
+    unsigned char a_hi[A_BYTES], a_lo[A_BYTES];
+    unsigned char b_hi[2][B_BYTES], b_lo[2][B_BYTES];
+    float list_v[KMAX][BM];
+    int list_i[KMAX][BM];
+    uint64_t full[2], empty[2], tfull[2], tempty[2];
+    uint32_t tmem_base;
+};
+
+// Rare path, kept out of line: the epilogue loop is unrolled over 64 columns and an inlined insertion
+// per column made the loop body 64 KB of code (ncu: 20 % of all samples were instruction-fetch stalls).
+__device__ __noinline__ void list_insert(Smem &S, int m, int k, float sc, int id) {
+    int pos = k - 1;
+    while (pos > 0) {
+        const float pv = S.list_v[pos - 1][m];
+        const int pi = S.list_i[pos - 1][m];
+        if (pv > sc || (pv == sc && pi < id)) break;
+        S.list_v[pos][m] = pv;
+        S.list_i[pos][m] = pi;
+        --pos;
+    }
+    S.list_v[pos][m] = sc;
+    S.list_i[pos][m] = id;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+score_topk_tc_kernel(const float *__restrict__ user_emb, const float *__restrict__ item_emb, int64_t num_items,
+                     int64_t u_begin, int64_t u_end, int normalize, const int64_t *__restrict__ excl_ptr,
+                     const int32_t *__restrict__ excl_idx, int k, int32_t *__restrict__ topk_idx,
+                     float *__restrict__ topk_val) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t u0 = u_begin + (int64_t)blockIdx.x * BM;
+    const int num_tiles = (int)((num_items + BN - 1) / BN);
+
+    // ---- one-time setup ------------------------------------------------------------------------
+    for (int grp = warp; grp < BM / 8; grp += THREADS / 32)
+        load_rows8(user_emb, u0, u_end, normalize != 0, S.a_hi, S.a_lo, grp, lane);
+    for (int x = tid; x < KMAX * BM; x += THREADS) {
+        (&S.list_v[0][0])[x] = -CUDART_INF_F;
+        (&S.list_i[0][0])[x] = INT_MAX;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&S.full[s], NUM_PROD);
+            mbar_init(&S.empty[s], 1);
+            mbar_init(&S.tfull[s], 1);
+            mbar_init(&S.tempty[s], NUM_EPI / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(&S.tmem_base)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // A tile (generic stores) -> async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = S.tmem_base;
+
+    if (warp >= 5) {
+        // ===== producers: item tiles -> shared memory (hi / lo halves) ============================
+        const int pw = warp - 5;
+        for (int t = 0; t < num_tiles; ++t) {
+            const int s = t & 1;
+            mbar_wait(&S.empty[s], ((t >> 1) & 1) ^ 1);
+            const int64_t n0 = (int64_t)t * BN;
+#pragma unroll
+            for (int it = 0; it < 2; ++it)
+                load_rows8(item_emb, n0, num_items, normalize != 0, S.b_hi[s], S.b_lo[s], pw * 2 + it, lane);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&S.full[s]);
+        }
+    } else if (warp == 4) {
+        // ===== MMA issuer ===========================================================================
+        if (lane == 0) {
+            const uint32_t a_hi = smem_u32(S.a_hi), a_lo = smem_u32(S.a_lo);
+            for (int t = 0; t < num_tiles; ++t) {
+                const int s = t & 1;
+                const uint32_t ph = (t >> 1) & 1;
+                mbar_wait(&S.full[s], ph);
+                mbar_wait(&S.tempty[s], ph ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem + (uint32_t)(s * BN);
+                const uint32_t b_hi = smem_u32(S.b_hi[s]), b_lo = smem_u32(S.b_lo[s]);
+#pragma unroll
+                for (int j = 0; j < BK / 8; ++j) {             // one MMA K-step = 8 tf32 = two 16-byte chunks
+                    const uint32_t ko = (uint32_t)j * 256u;
+                    umma_tf32(d, umma_desc(a_hi + ko), umma_desc(b_hi + ko), j > 0 ? 1u : 0u);
+                    umma_tf32(d, umma_desc(a_hi + ko), umma_desc(b_lo + ko), 1u);
+                    umma_tf32(d, umma_desc(a_lo + ko), umma_desc(b_hi + ko), 1u);
+                }
+                umma_commit(&S.empty[s]);                      // smem stage free once these MMAs have read it
+                umma_commit(&S.tfull[s]);                      // accumulator stage ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: thread = user = TMEM lane ==================================================
+        const int m = tid;                                     // 0..127
+        const bool live = u0 + m < u_end;
+        int64_t ex_cur = 0, ex_end = 0;
+        if (live && excl_ptr) { ex_cur = excl_ptr[u0 + m]; ex_end = excl_ptr[u0 + m + 1]; }
+        float thr = -CUDART_INF_F;
+        int thr_id = INT_MAX;
+        for (int t = 0; t < num_tiles; ++t) {
+            const int s = t & 1;
+            mbar_wait(&S.tfull[s], (t >> 1) & 1);
+            __syncwarp();                                       // reconverge: tcgen05.ld is .sync.aligned
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r[BN];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * BN);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+                "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+                  "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                  "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+                  "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]),
+                  "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]),
+                  "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.tempty[s]);           // accumulator stage may be overwritten
+            if (!live) continue;
+            const int64_t n0 = (int64_t)t * BN;
+            unsigned long long mask = 0ull;                     // train items of this user inside the tile
+            while (ex_cur < ex_end) {
+                const int64_t it = excl_idx[ex_cur];
+                if (it >= n0 + BN) break;
+                if (it >= n0) mask |= 1ull << (int)(it - n0);
+                ++ex_cur;
+            }
+            const int valid = (int)min((int64_t)BN, num_items - n0);
+            const unsigned long long admissible = (valid >= 64 ? ~0ull : ((1ull << valid) - 1ull)) & ~mask;
+#pragma unroll
+            for (int c = 0; c < BN; ++c) {
+                const float sc = __uint_as_float(r[c]);
+                if (((admissible >> c) & 1ull) && sc >= thr) {
+                    const int id = (int)(n0 + c);
+                    if (sc > thr || id < thr_id) {              // ranks before the current k-th entry
+                        list_insert(S, m, k, sc, id);
+                        thr = S.list_v[k - 1][m];
+                        thr_id = S.list_i[k - 1][m];
+                    }
+                }
+            }
+        }
+        if (live) {
+            const int64_t out = (u0 - u_begin + m) * (int64_t)k;
+            for (int e = 0; e < k; ++e) {
+                const float v = S.list_v[e][m];
+                topk_val[out + e] = v;
+                topk_idx[out + e] = v == -CUDART_INF_F ? -1 : S.list_i[e][m];
+            }
+        }
+    }
+    // ---- teardown ------------------------------------------------------------------------------
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace tc
+
+int score_topk_tc_impl(const float *ue, const float *ie, int64_t I, int64_t ub, int64_t uend, int normalize,
+                       const int64_t *ep, const int32_t *ex, int k, int32_t *ti, float *tv, cudaStream_t st) {
+    const size_t smem = sizeof(tc::Smem) + 1024;
+    LGCN_CUDA(cudaFuncSetAttribute(tc::score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = cdiv(uend - ub, tc::BM);
+    tc::score_topk_tc_kernel<<<grid, tc::THREADS, smem, st>>>(ue, ie, I, ub, uend, normalize, ep, ex, k, ti, tv);
+    LGCN_LAUNCH_CHECK();
+    return LGCN_OK;
+}
+
+}  // namespace lgcn
