@@ -61,9 +61,10 @@ int lgcn_version(void);
 
 /* One warp task: edges [begin,end) of `row` in one of the two CSRs.  slot < 0: the task owns
  * the whole row.  slot >= 0: the row is split; this task writes partial `slot`, the row's
- * first partial is `slot - part`, and it has `nparts` of them. */
+ * first partial is `slot - part`, and it has `nparts` of them.  deg_in / deg_out: the row's
+ * in- and out-degree in this edge list, so a kernel that walks tasks needs no per-node array. */
 typedef struct lgcn_task {
-    int32_t row, begin, end, slot, part, nparts, pad0, pad1;
+    int32_t row, begin, end, slot, part, nparts, deg_in, deg_out;
 } lgcn_task;
 
 /* Device-resident, immutable description of one edge list (built once per edge list and
@@ -117,6 +118,31 @@ int lgcn_graph_sizes_query(int64_t num_nodes, int64_t num_edges, lgcn_graph_size
 int lgcn_graph_build(const int64_t *edge_index, int64_t num_edges, int64_t num_nodes,
                      int64_t num_users, lgcn_graph *g, void *workspace, size_t workspace_bytes,
                      void *stream);
+
+/* ---- K0b: many edge lists -> many graphs in one pass --------------------------------------
+ * A Cluster-GCN epoch hands the path ~100 small edge lists (data/dataset_handler.py:277-285 ->
+ * utils/train_test.py:86-88 `for batch in train_loader: batch.to(device)`).  lgcn_graph_build_batched
+ * builds the lgcn_graph of every list with a fixed number of launches and ONE stream sync; each
+ * graph is bit-identical to what lgcn_graph_build gives for that list alone.
+ *
+ *   edges      device int64: the lists back to back, list b = its contiguous [2,E_b] tensor
+ *              (E_b sources then E_b targets) at int64 offset 2*edge_off[b]
+ *   edge_off   HOST int64 [B+1], edge_off[0] = 0, ascending (edge counts prefix sum)
+ *   graphs     HOST lgcn_graph [B], completely filled on return; all pointers point into `arena`,
+ *              which must stay alive as long as the graphs are used
+ *   workspace  scratch, free again when the call returns
+ * The B graphs SHARE partials / slot_counters / sched: use them one after another on one stream.
+ * LGCN_E_RANGE when B*(N+1) or the total edge count exceed int32: build in chunks of lists. */
+typedef struct lgcn_batched_sizes {
+    size_t arena_bytes;
+    size_t workspace_bytes;
+} lgcn_batched_sizes;
+
+int lgcn_graph_batched_sizes(int64_t num_nodes, int64_t num_lists, const int64_t *edge_off,
+                             lgcn_batched_sizes *out);
+int lgcn_graph_build_batched(const int64_t *edges, const int64_t *edge_off, int64_t num_lists,
+                             int64_t num_nodes, int64_t num_users, lgcn_graph *graphs, void *arena,
+                             size_t arena_bytes, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- K1/K2: propagation ----------------------------------------------------------------- */
 
@@ -247,6 +273,8 @@ typedef struct lgcn_step_buffers {
     int32_t *neg_flag;     /* [I] zero-initialised: last step in which the item was a negative */
     int32_t *neg_list;     /* [I] distinct INACTIVE negative items of the current step          */
     int32_t *neg_list_count; /* [1]                                                              */
+    /* lgcn_train_steps_sparse only */
+    int32_t *act_stamp;    /* [N] zero-initialised: last step in which the node had an incident edge */
 } lgcn_step_buffers;
 
 /* utils/train_test.py:88-96 for one batch: forward, BPR loss, backward, clip, Adam.
@@ -265,6 +293,20 @@ int lgcn_train_step(const lgcn_graph *g, float *user_w, float *item_w, int num_l
 int lgcn_train_step_sparse(const lgcn_graph *g, float *user_w, float *item_w, int num_layers,
                            const int64_t *neg, float bpr_coeff, const lgcn_adam *opt,
                            const lgcn_step_buffers *buf, float *loss_out, void *stream);
+
+/* A RUN of sparse steps in one persistent cooperative launch (epoch_kernel.cu): the loop
+ * `for batch in train_loader:` of utils/train_test.py:86-101 for `num_steps` consecutive batches.
+ * graphs: HOST array of built graphs (lgcn_graph_build / lgcn_graph_build_batched), every one with
+ * num_triplets > 0; neg: device int64, the steps' negatives back to back (step b has
+ * graphs[b].num_triplets of them); loss_out: device float [num_steps]; workspace: device,
+ * lgcn_train_steps_workspace_bytes(num_steps).  Same arithmetic and invariants as
+ * lgcn_train_step_sparse; additionally needs buf->act_stamp.  buf->trip_scratch must hold
+ * 2 * max_b num_triplets floats.  Does not synchronise. */
+size_t lgcn_train_steps_workspace_bytes(int64_t num_steps);
+int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_steps, float *user_w, float *item_w,
+                            int num_layers, const int64_t *neg, float bpr_coeff, const lgcn_adam *opt,
+                            const lgcn_step_buffers *buf, float *loss_out, void *workspace,
+                            size_t workspace_bytes, void *stream);
 
 /* Brings every row up to the current step (replays the pending zero-gradient updates). */
 int lgcn_adam_flush(const lgcn_adam *opt, float *user_w, float *item_w, int64_t num_users,

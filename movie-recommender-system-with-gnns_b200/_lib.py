@@ -28,7 +28,8 @@ EXPORTS = [
     "lgcn_cluster_extract_workspace_bytes", "lgcn_cluster_extract", "lgcn_score_topk",
     "lgcn_spmm", "lgcn_bpr_rows", "lgcn_prescale", "lgcn_fwd_layer", "lgcn_bwd_layer",
     "lgcn_bpr_fwd_bwd_range", "lgcn_clip_adam_rows", "lgcn_train_step_sparse", "lgcn_adam_flush",
-    "lgcn_peer_barrier", "lgcn_score_topk_ex",
+    "lgcn_peer_barrier", "lgcn_score_topk_ex", "lgcn_graph_batched_sizes", "lgcn_graph_build_batched",
+    "lgcn_train_steps_workspace_bytes", "lgcn_train_steps_sparse",
 ]
 
 
@@ -37,7 +38,7 @@ class LgcnError(RuntimeError):
 
 
 class CTask(Structure):
-    _fields_ = [(n, c_int32) for n in ("row", "begin", "end", "slot", "part", "nparts", "pad0", "pad1")]
+    _fields_ = [(n, c_int32) for n in ("row", "begin", "end", "slot", "part", "nparts", "deg_in", "deg_out")]
 
 
 class CGraph(Structure):
@@ -60,6 +61,10 @@ class CGraphSizes(Structure):
                                         "partial_bytes", "counter_bytes", "workspace_bytes", "active_list_bytes")]
 
 
+class CBatchedSizes(Structure):
+    _fields_ = [("arena_bytes", c_size_t), ("workspace_bytes", c_size_t)]
+
+
 class CAdam(Structure):
     _fields_ = [("lr", c_double), ("beta1", c_double), ("beta2", c_double), ("eps", c_double),
                 ("max_norm", c_double), ("step", c_void_p), ("m", c_void_p), ("v", c_void_p),
@@ -74,7 +79,8 @@ class CStepBuffers(Structure):
     _fields_ = [("final_emb", c_void_p), ("rnorm", c_void_p), ("grad_final", c_void_p), ("grad_e0", c_void_p),
                 ("work", c_void_p), ("work_bytes", c_size_t), ("neg_count", c_void_p),
                 ("trip_scratch", c_void_p), ("accum", c_void_p),
-                ("neg_flag", c_void_p), ("neg_list", c_void_p), ("neg_list_count", c_void_p)]
+                ("neg_flag", c_void_p), ("neg_list", c_void_p), ("neg_list_count", c_void_p),
+                ("act_stamp", c_void_p)]
 
 
 _lib = None
@@ -129,9 +135,16 @@ def lib():
     L.lgcn_peer_barrier.argtypes = [POINTER(CPeers), c_void_p, c_void_p, c_void_p]
     L.lgcn_train_step_sparse.argtypes = L.lgcn_train_step.argtypes
     L.lgcn_adam_flush.argtypes = [POINTER(CAdam), c_void_p, c_void_p, c_int64, c_int64, c_void_p]
+    L.lgcn_graph_batched_sizes.argtypes = [c_int64, c_int64, c_void_p, POINTER(CBatchedSizes)]
+    L.lgcn_graph_build_batched.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t,
+                                           c_void_p, c_size_t, c_void_p]
+    L.lgcn_train_steps_workspace_bytes.argtypes = [c_int64]
+    L.lgcn_train_steps_workspace_bytes.restype = c_size_t
+    L.lgcn_train_steps_sparse.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_float, POINTER(CAdam),
+                                          POINTER(CStepBuffers), c_void_p, c_void_p, c_size_t, c_void_p]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("lgcn_last_error", "lgcn_cluster_extract_workspace_bytes"):
+        if name not in ("lgcn_last_error", "lgcn_cluster_extract_workspace_bytes", "lgcn_train_steps_workspace_bytes"):
             fn.restype = c_int
     _lib = L
     return L
@@ -228,6 +241,75 @@ class Graph:
         return (self.out_ptr[1:] - self.out_ptr[:-1]).to(torch.int64)
 
 
+class GraphView:
+    """One graph of a BatchedGraphs build: the same duck type the step functions take from ``Graph``
+    (``ref``, ``c``, the counts); its arrays are slices of the build's arena (``array(name)`` gives a
+    tensor view for the parity tests)."""
+
+    def __init__(self, owner: "BatchedGraphs", c: CGraph, num_users: int, num_items: int):
+        self.owner, self.c = owner, c
+        self.device = owner.device
+        self.num_users, self.num_items, self.num_nodes = num_users, num_items, num_users + num_items
+        self.num_edges = int(c.num_edges)
+        self.num_triplets = int(c.num_triplets)
+        self.num_active = int(c.num_active)
+
+    @property
+    def ref(self):
+        return byref(self.c)
+
+    def array(self, name: str) -> torch.Tensor:
+        c, n, e = self.c, self.num_nodes, self.num_edges
+        spec = {"in_ptr": (n + 1, torch.int32), "out_ptr": (n + 1, torch.int32),
+                "in_nbr": (e, torch.int32), "in_trip": (e, torch.int32),
+                "out_nbr": (e, torch.int32), "out_trip": (e, torch.int32),
+                "dis": (n, torch.float32), "active": (n, torch.uint8),
+                "in_tasks": (c.n_in_tasks * 8, torch.int32), "out_tasks": (c.n_out_tasks * 8, torch.int32),
+                "active_list": (c.num_active, torch.int32)}[name]
+        off = getattr(c, name) - self.owner.arena.data_ptr()
+        nbytes = spec[0] * torch.empty((), dtype=spec[1]).element_size()
+        return self.owner.arena[off: off + nbytes].view(spec[1])
+
+
+class BatchedGraphs:
+    """K0b: the graphs of B edge lists built by ONE ``lgcn_graph_build_batched`` call.
+
+    ``edges``: device int64, the lists back to back (list b = its [2,E_b] tensor flattened at offset
+    ``2*edge_off[b]``); ``edge_off``: B+1 ascending ints starting at 0.  ``arena`` / ``workspace``
+    (uint8 CUDA tensors) are reused when large enough -- pass the previous build's to avoid
+    re-allocating every epoch.  The graphs share scratch: use them one after another on one stream."""
+
+    def __init__(self, edges: torch.Tensor, edge_off, num_users: int, num_items: int,
+                 arena: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+        require_cuda(edges, "edges", torch.int64)
+        dev = edges.device
+        self.device = dev
+        off = (c_int64 * len(edge_off))(*[int(x) for x in edge_off])
+        b = len(edge_off) - 1
+        n = num_users + num_items
+        if edges.numel() < 2 * int(edge_off[-1]):
+            raise LgcnError(f"edges holds {edges.numel()} ids, edge_off needs {2 * int(edge_off[-1])}")
+        L = lib()
+        sz = CBatchedSizes()
+        check(L.lgcn_graph_batched_sizes(n, b, off, byref(sz)))
+        if arena is None or arena.numel() < sz.arena_bytes:
+            arena = torch.empty(int(sz.arena_bytes * 1.25) + 256, dtype=torch.uint8, device=dev)
+        if workspace is None or workspace.numel() < sz.workspace_bytes:
+            workspace = torch.empty(int(sz.workspace_bytes * 1.25) + 256, dtype=torch.uint8, device=dev)
+        self.arena, self.workspace, self.edges = arena, workspace, edges
+        cg = (CGraph * b)()
+        check(L.lgcn_graph_build_batched(edges.data_ptr(), off, b, n, num_users, cg, arena.data_ptr(), arena.numel(),
+                                         workspace.data_ptr(), workspace.numel(), stream_ptr(dev)))
+        self._cg = cg
+        self.graphs = [GraphView(self, cg[i], num_users, num_items) for i in range(b)]
+
+    def __len__(self):
+        return len(self.graphs)
+
+    def __getitem__(self, i) -> GraphView:
+        return self.graphs[i]
+
+
 class StepBuffers:
     """Scratch for one forward/backward pass (reused across steps; sized for the largest P seen)."""
 
@@ -247,6 +329,8 @@ class StepBuffers:
         self.neg_flag = torch.zeros(num_items, dtype=torch.int32, device=device)
         self.neg_list = torch.zeros(num_items, dtype=torch.int32, device=device)
         self.neg_list_count = torch.zeros(1, dtype=torch.int32, device=device)
+        self.act_stamp = torch.zeros(num_nodes, dtype=torch.int32, device=device)     # lgcn_train_steps_sparse
+        self.steps_ws = torch.empty(0, dtype=torch.uint8, device=device)
         self.grad_final.zero_()            # the sparse step keeps dL/dfinal all-zero between steps
         self.c = CStepBuffers()
         self._fill()
@@ -260,6 +344,7 @@ class StepBuffers:
         c.trip_scratch = self.trip_scratch.data_ptr()
         c.neg_flag, c.neg_list = self.neg_flag.data_ptr(), self.neg_list.data_ptr()
         c.neg_list_count = self.neg_list_count.data_ptr()
+        c.act_stamp = self.act_stamp.data_ptr()
 
     def ensure_triplets(self, p: int):
         if self.trip_scratch.numel() < 2 * p:

@@ -81,22 +81,24 @@ __global__ void node_kernel(const int *__restrict__ in_ptr, const int *__restric
     slot_out[n] = pout > 1 ? pout : 0;
 }
 
-__global__ void task_kernel(const int *__restrict__ ptr, const int *__restrict__ task_off,
+__global__ void task_kernel(const int *__restrict__ ptr, const int *__restrict__ in_ptr,
+                            const int *__restrict__ out_ptr, const int *__restrict__ task_off,
                             const int *__restrict__ slot_off, int64_t N, int split, lgcn_task *__restrict__ tasks) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const int cnt = task_off[n + 1] - task_off[n];
     if (cnt == 0) return;
     const int b = ptr[n], e = ptr[n + 1];
+    const int din = in_ptr[n + 1] - in_ptr[n], dout = out_ptr[n + 1] - out_ptr[n];
     lgcn_task *t = tasks + task_off[n];
     if (cnt == 1) {
-        t[0] = lgcn_task{(int)n, b, e, -1, 0, 1, 0, 0};
+        t[0] = lgcn_task{(int)n, b, e, -1, 0, 1, din, dout};
         return;
     }
     const int s0 = slot_off[n];
     for (int i = 0; i < cnt; ++i) {
         const int tb = b + i * split;
-        t[i] = lgcn_task{(int)n, tb, min(e, tb + split), s0 + i, i, cnt, 0, 0};
+        t[i] = lgcn_task{(int)n, tb, min(e, tb + split), s0 + i, i, cnt, din, dout};
     }
 }
 
@@ -244,9 +246,9 @@ extern "C" int lgcn_graph_build(const int64_t *edge_index, int64_t E, int64_t N,
         size_t tb = w.cub_bytes;
         LGCN_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, scans[i], scans[i], (int)(N + 1), st));
     }
-    task_kernel<<<gN, T, 0, st>>>(in_ptr, w.cnt_in, w.slot_in, N, split, (lgcn_task *)g->in_tasks);
+    task_kernel<<<gN, T, 0, st>>>(in_ptr, in_ptr, out_ptr, w.cnt_in, w.slot_in, N, split, (lgcn_task *)g->in_tasks);
     LGCN_LAUNCH_CHECK();
-    task_kernel<<<gN, T, 0, st>>>(out_ptr, w.cnt_out, w.slot_out, N, split, (lgcn_task *)g->out_tasks);
+    task_kernel<<<gN, T, 0, st>>>(out_ptr, in_ptr, out_ptr, w.cnt_out, w.slot_out, N, split, (lgcn_task *)g->out_tasks);
     LGCN_LAUNCH_CHECK();
     active_list_kernel<<<gN, T, 0, st>>>(g->active, w.act32, N, (int *)g->active_list);
     LGCN_LAUNCH_CHECK();

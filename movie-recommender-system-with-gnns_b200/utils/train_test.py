@@ -17,7 +17,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from .._lib import CAdam, DIM, LgcnError, StepBuffers, check, lib, require_cuda, stream_ptr
+from .._lib import BatchedGraphs, CAdam, CGraph, DIM, LgcnError, StepBuffers, check, lib, require_cuda, stream_ptr
 from .helpers import get_triplets_indices, sample_negative
 
 
@@ -27,6 +27,11 @@ from .helpers import get_triplets_indices, sample_negative
 
 SPARSE_STEPS = True      # train(): use the touched-rows step for small batches (set False to force dense)
 CUDA_GRAPHS = True       # train(): replay each batch's step as one CUDA graph from its second epoch on
+EPOCH_KERNEL = True      # train(): consecutive sparse steps run inside ONE persistent cooperative launch
+STAGED_HOST_BATCHES = True   # train(): host-resident batches are uploaded and built together (K0b)
+STAGE_MAX_LISTS = 1024       # per lgcn_graph_build_batched call
+STAGE_MAX_CELLS = 1 << 27    # lists x (N+1)
+STAGE_MAX_EDGES = 1 << 27
 
 
 class _BprRows(torch.autograd.Function):
@@ -102,6 +107,7 @@ class FusedAdam:
         self._bc_table(1 << 18)
         self.buffers = StepBuffers(n, model.num_items, model.num_layers, w.device)
         self.losses = torch.zeros(8192, dtype=torch.float32, device=w.device)   # per-batch losses (see train)
+        self.stage = _Stage()         # device/pinned buffers of the host-batch pipeline (see _run_staged)
         self.c = CAdam()
         self._fill()
 
@@ -124,10 +130,10 @@ class FusedAdam:
         c.bc_table, c.bc_len = self.bc_table.data_ptr(), self.bc_table.shape[0]
         c.row_step = self.row_step.data_ptr()
 
-    def _count_step(self):
-        self.host_steps += 1
+    def _count_step(self, n: int = 1):
+        self.host_steps += n
         if self.host_steps + 2 >= self.bc_table.shape[0]:
-            self._bc_table(2 * self.bc_table.shape[0])
+            self._bc_table(2 * max(self.bc_table.shape[0], self.host_steps + 2))
             self._fill()
             self.graphs.clear()           # captured launches hold the old table address
             self.captured = 0
@@ -162,8 +168,17 @@ class FusedAdam:
         self.host_steps = int(self.step_count)
         self.row_step.fill_(self.host_steps)
         self.pending = False
+        self.buffers.neg_flag.zero_()     # step stamps of another timeline
+        self.buffers.act_stamp.zero_()
         self._bc_table(max(1 << 16, 2 * self.host_steps + 4))
         self._fill()
+
+
+class _Stage:
+    """Buffers the host-batch pipeline reuses from epoch to epoch (no per-epoch cudaMalloc)."""
+
+    def __init__(self):
+        self.edges = self.arena = self.workspace = self.pinned = self.current = None
 
 
 def train_step(model, optimizer: FusedAdam, edge_index: torch.Tensor, neg: Optional[torch.Tensor] = None,
@@ -203,12 +218,151 @@ def train_step(model, optimizer: FusedAdam, edge_index: torch.Tensor, neg: Optio
 
 
 def _launch_step(model, optimizer, g, neg, loss_out, bpr_coeff, sparse):
+    _launch_step_raw(model, optimizer, g, neg.data_ptr(), loss_out.data_ptr(), bpr_coeff, sparse, stream_ptr(neg.device))
+
+
+def _launch_step_raw(model, optimizer, g, neg_ptr, loss_ptr, bpr_coeff, sparse, stream):
     uw, iw = model.user_embedding.weight, model.item_embedding.weight
     fn = lib().lgcn_train_step_sparse if sparse else lib().lgcn_train_step
     if not sparse:
         optimizer.dirty = True
-    check(fn(g.ref, uw.data_ptr(), iw.data_ptr(), model.num_layers, neg.data_ptr(), bpr_coeff, byref(optimizer.c),
-             optimizer.buffers.ref, loss_out.data_ptr(), stream_ptr(neg.device)))
+    check(fn(g.ref, uw.data_ptr(), iw.data_ptr(), model.num_layers, neg_ptr, bpr_coeff, byref(optimizer.c),
+             optimizer.buffers.ref, loss_ptr, stream))
+
+
+class _SparseRun:
+    """Consecutive sparse steps waiting to be launched as ONE lgcn_train_steps_sparse call."""
+
+    def __init__(self, model, optimizer, device, weights, slots, cap):
+        self.model, self.opt, self.device = model, optimizer, device
+        self.weights, self.slots, self.cap = weights, slots, cap
+        self.graphs, self.edges = [], []
+
+    def add(self, g, num_edges: int):
+        self.graphs.append(g)
+        self.edges.append(num_edges)
+
+    def flush(self):
+        if not self.graphs:
+            return
+        b = len(self.graphs)
+        slot0 = len(self.weights)
+        if slot0 + b > self.cap:
+            raise LgcnError(f"more than {self.cap} batches in one epoch: enlarge FusedAdam.losses")
+        _launch_steps(self.model, self.opt, self.graphs, None, self.opt.losses.data_ptr() + 4 * slot0, 5e-3, self.device)
+        self.weights.extend(self.edges)
+        self.slots.extend(range(slot0, slot0 + b))
+        self.graphs, self.edges = [], []
+
+
+def _launch_steps(model, opt, graphs, neg_all, loss_ptr, bpr_coeff, device) -> None:
+    """One lgcn_train_steps_sparse call for ``graphs`` (all with triplets); ``neg_all``: the steps'
+    negatives back to back, sampled here when None."""
+    b = len(graphs)
+    trip = [g.num_triplets for g in graphs]
+    if min(trip) <= 0:
+        raise LgcnError("a batch has no user->movie edge: the reference's loss is NaN here (SURVEY App. B #13)")
+    if neg_all is None:
+        neg_all = torch.randint(0, model.num_items, (sum(trip),), device=device)
+    require_cuda(neg_all, "neg", torch.int64)
+    if neg_all.numel() != sum(trip):
+        raise LgcnError(f"neg has {neg_all.numel()} entries, the batches have {sum(trip)} user->movie edges")
+    buf = opt.buffers
+    buf.ensure_triplets(max(trip))
+    L = lib()
+    need = L.lgcn_train_steps_workspace_bytes(b)
+    if buf.steps_ws.numel() < need:
+        buf.steps_ws = torch.empty(2 * need, dtype=torch.uint8, device=device)
+    if opt.dirty:                      # dense steps leave dL/dfinal / the histogram dirty
+        buf.grad_final.zero_()
+        buf.neg_count.zero_()
+        opt.dirty = False
+    opt.pending = True
+    opt._count_step(b)
+    cg = (CGraph * b)(*[g.c for g in graphs])
+    uw, iw = model.user_embedding.weight, model.item_embedding.weight
+    if not (uw.is_contiguous() and iw.is_contiguous()):
+        raise LgcnError("embedding weights must be contiguous")
+    check(L.lgcn_train_steps_sparse(cg, b, uw.data_ptr(), iw.data_ptr(), model.num_layers, neg_all.contiguous().data_ptr(),
+                                    bpr_coeff, byref(opt.c), buf.ref, loss_ptr, buf.steps_ws.data_ptr(),
+                                    buf.steps_ws.numel(), stream_ptr(device)))
+
+
+def train_steps(model, optimizer: FusedAdam, edge_indices: Sequence[torch.Tensor],
+                negs: Optional[Sequence[torch.Tensor]] = None, bpr_coeff: float = 5e-3) -> torch.Tensor:
+    """``train_step(..., sparse=True)`` for a whole sequence of batches in ONE persistent launch
+    (``lgcn_train_steps_sparse``): the loop of utils/train_test.py:86-96 over ``edge_indices`` in order.
+    Returns the per-batch losses as a DEVICE tensor (no sync).  Rows the batches do not touch keep their
+    zero-gradient Adam updates pending (``optimizer.flush()``)."""
+    graphs = [model.graph(ei) for ei in edge_indices]
+    dev = edge_indices[0].device
+    neg_all = None if negs is None else torch.cat([n.reshape(-1) for n in negs])
+    if negs is not None:
+        for g, n in zip(graphs, negs):
+            if n.numel() != g.num_triplets:
+                raise LgcnError(f"neg has {n.numel()} entries, the batch has {g.num_triplets} user->movie edges")
+    losses = torch.empty(len(graphs), dtype=torch.float32, device=dev)
+    _launch_steps(model, optimizer, graphs, neg_all, losses.data_ptr(), bpr_coeff, dev)
+    return losses
+
+
+def _run_staged(model, optimizer: "FusedAdam", eis, device, weights, slots, cap) -> None:
+    """The loop body of utils/train_test.py:86-101 for a run of HOST-resident batches:
+    ``batch.to(device)`` becomes one upload of all the edge lists (straight from pinned tensors, or packed
+    through a pinned staging buffer), the per-batch normalisation / CSR becomes ONE batched build (K0b),
+    the negatives of a run of steps come from one ``randint`` (utils/helpers.py:79-80: uniform, no
+    rejection; neg k pairs with the k-th user->movie edge), then the steps run in loader order -- sparse
+    ones inside one persistent launch, dense ones one call each."""
+    st = optimizer.stage
+    sizes = [int(ei.shape[1]) for ei in eis]
+    off = np.zeros(len(eis) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=off[1:])
+    tot = int(off[-1])
+    if st.edges is None or st.edges.numel() < 2 * tot or st.edges.device != device:
+        st.edges = torch.empty(int(2.5 * tot) + 64, dtype=torch.int64, device=device)
+    flat = [ei.contiguous().reshape(-1) for ei in eis]
+    if all(f.is_pinned() for f in flat):
+        for f, o in zip(flat, off[:-1]):
+            st.edges[2 * int(o): 2 * int(o) + f.numel()].copy_(f, non_blocking=True)
+    else:
+        if st.pinned is None or st.pinned.numel() < 2 * tot:
+            st.pinned = torch.empty(int(2.5 * tot) + 64, dtype=torch.int64, pin_memory=True)
+        torch.cat(flat, out=st.pinned[: 2 * tot])
+        st.edges[: 2 * tot].copy_(st.pinned[: 2 * tot], non_blocking=True)
+    bg = BatchedGraphs(st.edges, off, model.num_users, model.num_items, st.arena, st.workspace)
+    st.arena, st.workspace, st.current = bg.arena, bg.workspace, bg
+    run = _SparseRun(model, optimizer, device, weights, slots, cap)
+    for g, e in zip(bg.graphs, sizes):
+        if g.num_triplets == 0:
+            continue                      # the reference would produce NaN here (App. B #13)
+        if EPOCH_KERNEL and sparse_step_pays(g):
+            run.add(g, e)
+            continue
+        run.flush()
+        _single_step(model, optimizer, g, e, device, weights, slots, cap)
+    run.flush()
+
+
+def _single_step(model, optimizer, g, num_edges, device, weights, slots, cap) -> None:
+    """One eager fused step (sparse or dense) on an already built graph, negatives sampled here."""
+    slot = len(weights)
+    if slot >= cap:
+        raise LgcnError(f"more than {cap} batches in one epoch: enlarge FusedAdam.losses")
+    sparse = sparse_step_pays(g)
+    neg = torch.randint(0, model.num_items, (g.num_triplets,), device=device)
+    optimizer.buffers.ensure_triplets(g.num_triplets)
+    optimizer._count_step()
+    if sparse:
+        if optimizer.dirty:
+            optimizer.buffers.grad_final.zero_()
+            optimizer.buffers.neg_count.zero_()
+            optimizer.dirty = False
+        optimizer.pending = True
+    else:
+        optimizer.flush()
+    _launch_step(model, optimizer, g, neg, optimizer.losses[slot:slot + 1], 5e-3, sparse)
+    weights.append(num_edges)
+    slots.append(slot)
 
 
 def sparse_step_pays(g) -> bool:
@@ -217,15 +371,41 @@ def sparse_step_pays(g) -> bool:
 
 
 def _train_epoch_fused(model, optimizer: "FusedAdam", train_loader, device) -> float:
-    """One epoch on the fused path.  Per batch: one C-ABI call (sparse or dense step); from the second
-    time a batch tensor is seen its whole step -- negative sampling included -- is replayed as ONE
-    CUDA graph launch (the reference's loader hands back the same tensors every epoch,
+    """One epoch on the fused path.  Batches that touch a small part of the table (Cluster-GCN) are
+    collected, in loader order, into runs that execute inside ONE persistent cooperative launch
+    (``lgcn_train_steps_sparse``); host-resident batches are first uploaded and built together
+    (``_run_staged``).  A dense batch is one C-ABI call, replayed as a CUDA graph from the second time its
+    tensor is seen (the reference's loader hands back the same tensors every epoch,
     data/dataset_handler.py:277-285).  The only host<->device sync is the loss read-back at the end."""
+    device = torch.device(device)
     weights, slots = [], []
     cap = optimizer.losses.numel() // 2          # [0,cap): this epoch's eager steps; [cap,2cap): captured graphs
     if len(optimizer.graphs) > cap:              # fresh tensors every epoch: forget the never-captured ones
         optimizer.graphs = {k: v for k, v in optimizer.graphs.items() if v[1] is not None}
+    pending, pending_edges = [], 0
+    run = _SparseRun(model, optimizer, device, weights, slots, cap)
+
+    def run_pending():
+        nonlocal pending, pending_edges
+        if pending:
+            run.flush()
+            _run_staged(model, optimizer, pending, device, weights, slots, cap)
+            pending, pending_edges = [], 0
+
     for batch in train_loader:
+        ei = batch.edge_index
+        if STAGED_HOST_BATCHES and not ei.is_cuda and device.type == "cuda":
+            if ei.shape[1] == 0:
+                continue
+            if ei.dtype != torch.int64 or ei.dim() != 2 or ei.size(0) != 2:
+                raise LgcnError(f"edge_index must be an int64 [2,E] tensor, got {ei.dtype} {tuple(ei.shape)}")
+            if (len(pending) + 1 > STAGE_MAX_LISTS or (len(pending) + 1) * (model.num_users + model.num_items + 1)
+                    > STAGE_MAX_CELLS or pending_edges + ei.shape[1] > STAGE_MAX_EDGES):
+                run_pending()
+            pending.append(ei)
+            pending_edges += ei.shape[1]
+            continue
+        run_pending()                     # keep the loader's order of optimiser steps
         batch = batch.to(device)
         ei = batch.edge_index
         if ei.shape[1] == 0:
@@ -238,6 +418,10 @@ def _train_epoch_fused(model, optimizer: "FusedAdam", train_loader, device) -> f
             optimizer.graph_generation, optimizer.captured = optimizer.buffers.generation, 0
         # Cluster-GCN batches touch a small part of the table: visit only those rows
         sparse = sparse_step_pays(g)
+        if sparse and EPOCH_KERNEL:
+            run.add(g, ei.shape[1])       # launched together with its neighbours in loader order
+            continue
+        run.flush()
         entry = optimizer.graphs.get(id(g)) if CUDA_GRAPHS else None
         if entry is not None and entry[0] is not g:
             entry = None
@@ -274,6 +458,8 @@ def _train_epoch_fused(model, optimizer: "FusedAdam", train_loader, device) -> f
                 optimizer.graphs[id(g)] = (g, None, None)
         weights.append(ei.shape[1])
         slots.append(slot)
+    run_pending()
+    run.flush()
     optimizer.flush()
     if not weights:
         return float("nan")

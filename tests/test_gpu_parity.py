@@ -372,6 +372,62 @@ def test_sparse_steps_equal_dense_steps_and_oracle(shape, parts, k):
     assert max_abs(us, st.user_w.detach()) < steps * ADAM_STEP_ATOL and max_abs(isp, st.item_w.detach()) < steps * ADAM_STEP_ATOL
 
 
+@pytest.mark.parametrize("shape,parts,k", [("ml100k", 6, 3), ("ml1m", 12, 2), ("ml100k", 5, 1), ("ml100k", 7, 4)])
+def test_persistent_steps_kernel_equals_sequential_sparse_steps_and_oracle(shape, parts, k):
+    """lgcn_train_steps_sparse (one cooperative launch for the whole run) vs one lgcn_train_step_sparse per
+    batch vs the CPU oracle, same negatives."""
+    g, train, _, u0, i0 = _case(shape)
+    batches = _cluster_like_batches(g, train, parts)
+    epochs = 2
+    negs = [[_negs(b, g.num_users, g.num_items, 77 * e + i) for i, b in enumerate(batches)] for e in range(epochs)]
+    dev_b = [b.to(DEV) for b in batches]
+    m1, m2 = _model(g.num_users, g.num_items, k, u0, i0), _model(g.num_users, g.num_items, k, u0, i0)
+    o1, o2 = tt.FusedAdam(m1), tt.FusedAdam(m2)
+    l1, l2 = [], []
+    for e in range(epochs):
+        dn = [n.to(DEV) for n in negs[e]]
+        l1.append(tt.train_steps(m1, o1, dev_b, dn).clone())
+        for b, n in zip(dev_b, dn):
+            l2.append(tt.train_step(m2, o2, b, n, sparse=True).clone())
+        assert o1.pending
+        o1.flush()
+        o2.flush()
+        assert int(o1.row_step.min()) == int(o1.step_count) == (e + 1) * len(batches)
+        assert float(o1.buffers.grad_final.abs().max()) == 0.0 and int(o1.buffers.neg_count.abs().max()) == 0
+    l1, l2 = torch.cat(l1).cpu(), torch.cat(l2).cpu()
+    assert float((l1 - l2).abs().max()) < 2e-6 * float(l2.abs().max())
+    steps = epochs * len(batches)
+    # the persistent kernel gathers pre-scaled tables (dis (.) x rounded once) where the per-step kernels
+    # fuse the scale into an fma: gradient noise ~1e-10, amplified by Adam like any other (tests/conftest.py)
+    assert max_abs(m1.user_embedding.weight, m2.user_embedding.weight) < steps * ADAM_STEP_ATOL
+    assert max_abs(m1.item_embedding.weight, m2.item_embedding.weight) < steps * ADAM_STEP_ATOL
+    assert normwise(o1.exp_avg, o2.exp_avg) < 1e-4 and normwise(o1.exp_avg_sq, o2.exp_avg_sq) < 1e-4
+    st = ref.TrainState(u0, i0, k)
+    want = [st.step(b, n) for e in range(epochs) for b, n in zip(batches, negs[e])]
+    assert max(abs(float(a) - w) / abs(w) for a, w in zip(l1, want)) < 1e-4
+    assert max_abs(m1.user_embedding.weight, st.user_w.detach()) < steps * ADAM_STEP_ATOL
+    assert max_abs(m1.item_embedding.weight, st.item_w.detach()) < steps * ADAM_STEP_ATOL
+
+
+def test_persistent_steps_kernel_mixes_with_single_steps_and_rejects_bad_runs():
+    g, train, k, u0, i0 = _case("ml100k")
+    batches = [b.to(DEV) for b in _cluster_like_batches(g, train, 6)]
+    m = _model(g.num_users, g.num_items, k, u0, i0)
+    opt = tt.FusedAdam(m)
+    tt.train_step(m, opt, train.to(DEV))                       # dense step: leaves dL/dfinal dirty
+    tt.train_steps(m, opt, batches[:3])
+    tt.train_step(m, opt, batches[3], sparse=True)
+    tt.train_steps(m, opt, batches[4:])
+    opt.flush()
+    assert int(opt.step_count) == 1 + len(batches) and int(opt.row_step.min()) == int(opt.step_count)
+    assert torch.isfinite(m.user_embedding.weight).all() and torch.isfinite(m.item_embedding.weight).all()
+    no_trip = train[:, train[0] >= g.num_users].contiguous().to(DEV)   # movie->user edges only
+    with pytest.raises(_lib.LgcnError):
+        tt.train_steps(m, opt, [batches[0], no_trip])
+    with pytest.raises(_lib.LgcnError):
+        tt.train_steps(m, opt, [batches[0]], [torch.zeros(3, dtype=torch.int64, device=DEV)])
+
+
 def test_train_epoch_uses_sparse_steps_and_flushes():
     from lgcn_b200.data.dataset_handler import ClusterLoader, Data
     g, train, k, u0, i0 = _case("ml100k")
@@ -380,9 +436,20 @@ def test_train_epoch_uses_sparse_steps_and_flushes():
     opt = tt.FusedAdam(m)
     torch.manual_seed(0)
     loader = ClusterLoader(parts, shuffle=True)
-    hist = [tt.train(m, opt, loader, DEV) for _ in range(4)]       # eager, capture, replay, replay
+    hist = [tt.train(m, opt, loader, DEV) for _ in range(4)]       # one persistent launch per epoch
     assert not opt.pending and int(opt.row_step.min()) == int(opt.step_count) == 4 * len(parts)
-    assert opt.captured == len(parts)
+    assert opt.captured == 0
+    # without the persistent kernel: eager, capture, replay, replay of per-batch CUDA graphs
+    tt.EPOCH_KERNEL = False
+    try:
+        m3 = _model(g.num_users, g.num_items, k, u0, i0)
+        opt3 = tt.FusedAdam(m3)
+        torch.manual_seed(0)
+        hist3 = [tt.train(m3, opt3, loader, DEV) for _ in range(4)]
+        assert opt3.captured == len(parts) and not opt3.pending
+    finally:
+        tt.EPOCH_KERNEL = True
+    assert max(abs(a - b) / abs(b) for a, b in zip(hist, hist3)) < 5e-2
     assert all(np.isfinite(h) for h in hist) and hist[3] < hist[2] < hist[1] < hist[0] < 0.0   # the loss goes down
     # the same four epochs without CUDA graphs / sparse steps give the same trajectory (negatives differ: RNG
     # streams are consumed differently under capture), so compare loosely
