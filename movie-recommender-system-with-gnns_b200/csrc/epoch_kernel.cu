@@ -23,6 +23,14 @@
 //   G  backward layers 1..K (barrier after each); the last also forms the inactive negatives' grad  |
 //   J  clip + Adam step on the touched rows, restore the all-zero invariants, loss, prefetch b+1    |
 //
+// CTAs are split in two roles.  MAIN CTAs run phases B..J, separated by barriers among themselves.
+// HELPER CTAs (a quarter of the grid) spend that time bringing the NEXT step's user rows up to date
+// ("early replay"): a user row is touched once per epoch, so ~100 zero-gradient Adam steps -- IEEE
+// sqrt and two divisions per element and step -- are pending when its cluster comes up; that arithmetic
+// (the same amount dense Adam performs) would otherwise sit on the critical path of phase A.  A row that
+// the current step touches itself is skipped (phase J brings it to the same step).  Everybody meets
+// after phase A and at the end of the step.
+//
 // Memory rules inside the kernel: everything another SM may have written earlier in the launch is read
 // with ld.global.cg (L2, the coherence point); __ldg only for data that is immutable for the whole
 // launch (task lists, index arrays, negatives, the bias-correction table).
@@ -63,7 +71,8 @@ struct EpochArgs {
     float *scratch;
     double *accum;       // [2][4], by step parity
     int32_t *counts;     // [2] length of neg_list, by step parity
-    unsigned *bar;       // [2] arrivals, generation
+    unsigned *bar;       // [0]: arrivals of all CTAs, [32]: arrivals of the main CTAs (monotonic counters)
+    int num_helpers;     // CTAs [gridDim.x - num_helpers, gridDim.x) replay the next step's user rows
     float bpr_coeff;
     long long *prof;     // optional [num_steps][16] globaltimer stamps at the phase boundaries (diagnostics)
 };
@@ -79,22 +88,17 @@ __device__ __forceinline__ void stamp(long long *prof, int b, int &slot, int gti
     ++slot;
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks) {
+// Arrive (release) on a monotonic counter, wait (acquire) until `count` more CTAs have arrived than at
+// the previous barrier on it.  bar.sync before/after extends the ordering to the whole CTA.
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned count) {
     __syncthreads();
+    target += count;
     if (threadIdx.x == 0) {
-        unsigned gen, cur;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
-        __threadfence();
-        if (atomicAdd(bar, 1u) == nblocks - 1) {
-            atomicExch(bar, 0u);
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar + 1) : "memory");
-            } while (cur == gen);
-        }
-        __threadfence();
+        unsigned cur;
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(bar), "r"(1u) : "memory");
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar) : "memory");
+        } while ((int)(cur - target) < 0);
     }
     __syncthreads();
 }
@@ -122,7 +126,7 @@ struct Nbr {
 __device__ __forceinline__ float dis_of(int deg_in) { return deg_in > 0 ? 1.0f / sqrtf((float)deg_in) : 0.f; }
 
 // raw[c] = sum over the task's edges of x[nbr]   (x written earlier in this launch -> ld.cg)
-__device__ __forceinline__ void gather_sum(const int32_t *__restrict__ nbr, const float *x, int begin, int end, int lane,
+__device__ __noinline__ void gather_sum(const int32_t *__restrict__ nbr, const float *x, int begin, int end, int lane,
                                            float4 &acc) {
     const int l16 = lane & 15;
     const float4 *x4 = reinterpret_cast<const float4 *>(x);
@@ -190,7 +194,10 @@ __device__ __forceinline__ float4 replay_row(bool valid, int row, int lane, int 
     const unsigned half_mask = 0xffffu << (lane & 16);
     const bool any_live = (__ballot_sync(FULL, live) & half_mask) != 0u;
     if (need && any_live) {
+        // iterations only chain through one fma each for p, m, v: unrolling lets the sqrt / division
+        // sequences of neighbouring steps overlap
         const float4 zero = f4zero();
+#pragma unroll 4
         for (int t = from + 1; t <= target; ++t) {
             const AdamScalars a = adam_scalars(h, t);
             adam_vec(p4, m4, v4, zero, 1.0f, a);
@@ -201,7 +208,41 @@ __device__ __forceinline__ float4 replay_row(bool valid, int row, int lane, int 
     return p4;
 }
 
-__device__ __forceinline__ void adam_row(int row, int lane, int t, const Tab &w, float4 *m, float4 *v, const float4 *grad,
+// The three row sets whose pending zero-gradient steps are replayed, behind ONE copy of the (unrolled)
+// Adam loop:  RP_ACTIVE  the step's active rows (in-tasks, first part): -> target, y0 = dis (.) e0, stamp
+//             RP_AHEAD   the NEXT step's user rows, unless the current step (stamp) updates them itself
+//             RP_LIST    rows `offset + list[i]` (the distinct inactive negatives)
+enum { RP_ACTIVE = 0, RP_AHEAD = 1, RP_LIST = 2 };
+
+__device__ __noinline__ void replay_rows(int mode, const lgcn_task *__restrict__ tasks, const int32_t *list, int count,
+                                         int offset, int target, int stamp_now, Tab w, float4 *m, float4 *v,
+                                         int32_t *row_step, int32_t *act_stamp, float *y0, AdamHyper h, int gw, int nw,
+                                         int lane) {
+    const int l16 = lane & 15, half = lane >> 4;
+    for (int base = gw * 2; base < count; base += nw * 2) {
+        const int i = base + half;
+        bool valid = i < count;
+        int row = 0, din = 0;
+        if (valid) {
+            if (mode == RP_LIST) {
+                row = offset + __ldcg(list + i);
+            } else {
+                const int4 ta = __ldg(reinterpret_cast<const int4 *>(tasks + i));
+                const int4 tc = __ldg(reinterpret_cast<const int4 *>(tasks + i) + 1);
+                row = ta.x; din = tc.z;
+                valid = tc.x == 0;                           // first part of a split row speaks for the row
+                if (mode == RP_AHEAD && valid) valid = __ldcg(act_stamp + row) != stamp_now;
+            }
+        }
+        const float4 p4 = replay_row(valid, row, lane, target, w, m, v, row_step, h);
+        if (mode == RP_ACTIVE && valid) {
+            reinterpret_cast<float4 *>(y0)[(size_t)row * D4 + l16] = f4scale(dis_of(din), p4);
+            if (l16 == 0) act_stamp[row] = stamp_now;
+        }
+    }
+}
+
+__device__ __noinline__ void adam_row(int row, int lane, int t, const Tab &w, float4 *m, float4 *v, const float4 *grad,
                                          float4 *G, int32_t *row_step, int32_t *neg_count, float clip,
                                          const AdamScalars &a) {
     const int l16 = lane & 15;
@@ -258,9 +299,15 @@ struct TripB {
 
 __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a) {
     const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
-    const int gw = blockIdx.x * EP_WARPS + (threadIdx.x >> 5), nw = gridDim.x * EP_WARPS;
-    const int gtid = blockIdx.x * EP_THREADS + threadIdx.x, nthreads = gridDim.x * EP_THREADS;
-    const unsigned nblocks = gridDim.x;
+    const int gw_all = blockIdx.x * EP_WARPS + (threadIdx.x >> 5), nw_all = gridDim.x * EP_WARPS;
+    const unsigned nblocks = gridDim.x, nmain = gridDim.x - a.num_helpers;
+    const bool helper = blockIdx.x >= nmain;
+    // main CTAs index their work among themselves; helpers among themselves
+    const int gw = helper ? gw_all - (int)nmain * EP_WARPS : gw_all;
+    const int nw = helper ? a.num_helpers * EP_WARPS : (int)nmain * EP_WARPS;
+    const int gtid = blockIdx.x * EP_THREADS + threadIdx.x, nthreads = (int)nmain * EP_THREADS;
+    unsigned tgt_all = 0, tgt_main = 0;
+    unsigned *const bar_all = a.bar, *const bar_main = a.bar + 32;
     const int K = a.K, U = a.num_users;
     const size_t n = (size_t)a.num_users + (size_t)a.num_items;
     const Tab w{a.user_w, a.item_w, U};
@@ -287,24 +334,21 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
             nx[0] = 0.0; nx[1] = 0.0; nx[2] = 0.0; nx[3] = 0.0;
             a.counts[(b + 1) & 1] = 0;
         }
-        for (int base = gw * 2; base < d.n_in_tasks; base += nw * 2) {
-            const int ti = base + half;
-            bool valid = ti < d.n_in_tasks;
-            int row = 0, din = 0;
-            if (valid) {
-                const int4 ta = __ldg(reinterpret_cast<const int4 *>(d.in_tasks + ti));
-                const int4 tc = __ldg(reinterpret_cast<const int4 *>(d.in_tasks + ti) + 1);
-                row = ta.x; din = tc.z;
-                valid = tc.x == 0;                           // first part of a split row speaks for the row
-            }
-            const float4 p4 = replay_row(valid, row, lane, t - 1, w, a.m, a.v, a.row_step, a.h);
-            if (valid) {
-                reinterpret_cast<float4 *>(y0)[(size_t)row * D4 + l16] = f4scale(dis_of(din), p4);
-                if (l16 == 0) a.act_stamp[row] = t;
-            }
-        }
-        grid_barrier(a.bar, nblocks);
+        replay_rows(RP_ACTIVE, d.in_tasks, nullptr, d.n_in_tasks, 0, t - 1, t, w, a.m, a.v, a.row_step, a.act_stamp, y0, a.h,
+                    gw_all, nw_all, lane);
+        grid_barrier(bar_all, tgt_all, nblocks);
         stamp(a.prof, b, ps, gtid);
+
+        if (helper) {
+            // ---- early replay: the next step's user rows -> step t (skipping rows this step updates itself)
+            if (b + 1 < a.num_steps) {
+                const StepDesc nx = a.steps[b + 1];
+                replay_rows(RP_AHEAD, nx.in_tasks, nullptr, nx.n_in_user_tasks, 0, t, t, w, a.m, a.v, a.row_step, a.act_stamp,
+                            nullptr, a.h, gw, nw, lane);
+            }
+            grid_barrier(bar_all, tgt_all, nblocks);     // end of the step
+            continue;
+        }
 
         // ---- B: distinct inactive negatives  +  forward layer 1 --------------------------------
         for (long long base = (long long)gw * 32; base < d.P; base += (long long)nw * 32) {
@@ -339,26 +383,15 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
                           }
                       });
         };
-        fwd_layer(1);
-        grid_barrier(a.bar, nblocks);
-        stamp(a.prof, b, ps, gtid);
-
-        // ---- C: negatives -> step t-1  +  forward layers 2..K ----------------------------------
-        {
-            const int cnt = __ldcg(cnt_cur);
-            for (int base = gw * 2; base < cnt; base += nw * 2) {
-                const int idx = base + half;
-                const bool valid = idx < cnt;
-                const int row = valid ? U + __ldcg(a.neg_list + idx) : 0;
-                replay_row(valid, row, lane, t - 1, w, a.m, a.v, a.row_step, a.h);
-            }
-        }
-        if (K == 1) grid_barrier(a.bar, nblocks);
-        stamp(a.prof, b, ps, gtid);
-        for (int k = 2; k <= K; ++k) {
-            fwd_layer(k);
-            grid_barrier(a.bar, nblocks);
-        stamp(a.prof, b, ps, gtid);
+        // ---- C: negatives -> step t-1 (any time between the first barrier below and phase E) ------
+        //      K == 1 has no second forward layer to share a phase with: one extra round of the loop
+        for (int k = 1; k <= (K == 1 ? 2 : K); ++k) {
+            if (k == 2)
+                replay_rows(RP_LIST, nullptr, a.neg_list, __ldcg(cnt_cur), U, t - 1, t, w, a.m, a.v, a.row_step, a.act_stamp,
+                            nullptr, a.h, gw, nw, lane);
+            if (k <= K) fwd_layer(k);
+            grid_barrier(bar_main, tgt_main, nmain);
+            stamp(a.prof, b, ps, gtid);
         }
 
         // ---- E: BPR over user rows -------------------------------------------------------------
@@ -430,7 +463,7 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
                       }
                   });
         if (lane == 0 && ex0 != 0.f) atomicAdd(acc_cur + 0, (double)ex0);
-        grid_barrier(a.bar, nblocks);
+        grid_barrier(bar_main, tgt_main, nmain);
         stamp(a.prof, b, ps, gtid);
 
         // ---- F: BPR over item rows -------------------------------------------------------------
@@ -470,7 +503,7 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
                           reinterpret_cast<float4 *>(Z1)[(size_t)row * D4 + l16] = f4scale(dis_of(din), cur);
                       }
                   });
-        grid_barrier(a.bar, nblocks);
+        grid_barrier(bar_main, tgt_main, nmain);
         stamp(a.prof, b, ps, gtid);
 
         // ---- G: backward layers 1..K (Horner); the last one also serves the inactive negatives ----
@@ -521,7 +554,7 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
                 if (lane == 0 && ex0 != 0.f) atomicAdd(acc_cur + 1, (double)ex0);
                 if (lane == 0 && ex1 != 0.f) atomicAdd(acc_cur + 2, (double)ex1);
             }
-            grid_barrier(a.bar, nblocks);
+            grid_barrier(bar_main, tgt_main, nmain);
         stamp(a.prof, b, ps, gtid);
         }
 
@@ -565,7 +598,7 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
                 }
             }
         }
-        grid_barrier(a.bar, nblocks);
+        grid_barrier(bar_all, tgt_all, nblocks);
         stamp(a.prof, b, ps, gtid);
     }
 }
@@ -578,7 +611,7 @@ static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 extern "C" size_t lgcn_train_steps_workspace_bytes(int64_t num_steps) {
     using namespace lgcn::ep;
     const size_t steps = (size_t)(num_steps > 0 ? num_steps : 1);
-    return align256(sizeof(StepDesc) * steps) + 256 + 128 * steps;       // descriptors, state, phase stamps
+    return align256(sizeof(StepDesc) * steps) + 512 + 128 * steps;       // descriptors, state, phase stamps
 }
 
 extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_steps, float *user_w, float *item_w, int K,
@@ -625,7 +658,7 @@ extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_ste
     const size_t desc_bytes = sizeof(StepDesc) * (size_t)num_steps;
     char *state = ws + align256(desc_bytes);
     LGCN_CUDA(cudaMemcpyAsync(ws, descs.data(), desc_bytes, cudaMemcpyHostToDevice, st));   // pageable: staged before return
-    LGCN_CUDA(cudaMemsetAsync(state, 0, 256, st));
+    LGCN_CUDA(cudaMemsetAsync(state, 0, 512, st));
 
     EpochArgs a{};
     a.steps = (const StepDesc *)ws;
@@ -636,10 +669,10 @@ extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_ste
     a.final_emb = buf->final_emb; a.rnorm = buf->rnorm; a.G = buf->grad_final; a.grad = buf->grad_e0; a.work = buf->work;
     a.neg_count = buf->neg_count; a.neg_flag = buf->neg_flag; a.neg_list = buf->neg_list; a.act_stamp = buf->act_stamp;
     a.scratch = buf->trip_scratch;
-    a.accum = (double *)state; a.counts = (int32_t *)(state + 64); a.bar = (unsigned *)(state + 128);
+    a.accum = (double *)state; a.counts = (int32_t *)(state + 64); a.bar = (unsigned *)(state + 128);   // bar[32] = state + 256
     a.bpr_coeff = bpr_coeff;
     static const bool want_prof = getenv("LGCN_EPOCH_PROF") != nullptr;   // tools/epoch_breakdown.py
-    a.prof = want_prof ? (long long *)(state + 256) : nullptr;
+    a.prof = want_prof ? (long long *)(state + 512) : nullptr;
 
     static int grid = 0;
     if (grid == 0) {
@@ -652,6 +685,9 @@ extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_ste
         LGCN_REQUIRE(per_sm >= 1, LGCN_E_CUDA, "train_steps_sparse: kernel does not fit on an SM");
         grid = sms;
     }
+    static const int helpers_env = getenv("LGCN_EPOCH_HELPERS") ? atoi(getenv("LGCN_EPOCH_HELPERS")) : -1;   // tuning aid
+    a.num_helpers = num_steps > 1 ? (helpers_env >= 0 ? helpers_env : 0) : 0;
+    if (a.num_helpers > grid - 1) a.num_helpers = grid - 1;
     void *params[] = {(void *)&a};
     LGCN_CUDA(cudaLaunchCooperativeKernel((const void *)epoch_kernel, dim3(grid), dim3(EP_THREADS), params, 0, st));
     return LGCN_OK;
