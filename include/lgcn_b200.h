@@ -274,7 +274,8 @@ typedef struct lgcn_step_buffers {
     int32_t *neg_list;     /* [I] distinct INACTIVE negative items of the current step          */
     int32_t *neg_list_count; /* [1]                                                              */
     /* lgcn_train_steps_sparse only */
-    int32_t *act_stamp;    /* [N] zero-initialised: last step in which the node had an incident edge */
+    int32_t *act_stamp;    /* [2*N + 4*I] zero-initialised: per step parity, the step in which a node is
+                            * active [2][N], an item is an inactive negative [2][I], and the list of those [2][I] */
 } lgcn_step_buffers;
 
 /* utils/train_test.py:88-96 for one batch: forward, BPR loss, backward, clip, Adam.
@@ -301,7 +302,8 @@ int lgcn_train_step_sparse(const lgcn_graph *g, float *user_w, float *item_w, in
  * graphs[b].num_triplets of them); loss_out: device float [num_steps]; workspace: device,
  * lgcn_train_steps_workspace_bytes(num_steps).  Same arithmetic and invariants as
  * lgcn_train_step_sparse; additionally needs buf->act_stamp.  buf->trip_scratch must hold
- * 2 * max_b num_triplets floats.  Does not synchronise. */
+ * 2 * max_b num_triplets floats; opt->bc_table must cover the steps of the run (current step +
+ * num_steps < bc_len).  Does not synchronise. */
 size_t lgcn_train_steps_workspace_bytes(int64_t num_steps);
 int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_steps, float *user_w, float *item_w,
                             int num_layers, const int64_t *neg, float bpr_coeff, const lgcn_adam *opt,

@@ -329,7 +329,7 @@ class StepBuffers:
         self.neg_flag = torch.zeros(num_items, dtype=torch.int32, device=device)
         self.neg_list = torch.zeros(num_items, dtype=torch.int32, device=device)
         self.neg_list_count = torch.zeros(1, dtype=torch.int32, device=device)
-        self.act_stamp = torch.zeros(num_nodes, dtype=torch.int32, device=device)     # lgcn_train_steps_sparse
+        self.act_stamp = torch.zeros(2 * num_nodes + 4 * num_items, dtype=torch.int32, device=device)   # lgcn_train_steps_sparse
         self.steps_ws = torch.empty(0, dtype=torch.uint8, device=device)
         self.grad_final.zero_()            # the sparse step keeps dL/dfinal all-zero between steps
         self.c = CStepBuffers()

@@ -38,6 +38,20 @@ __device__ __forceinline__ AdamScalars adam_scalars(const AdamHyper &h, long lon
     return a;
 }
 
+// Table-only variant for kernels whose caller guarantees t < bc_len (no inlined double pow()).
+__device__ __forceinline__ AdamScalars adam_scalars_tab(const AdamHyper &h, long long t) {
+    AdamScalars a;
+    const long long i = t < h.bc_len ? t : h.bc_len - 1;
+    const float2 s = __ldg(reinterpret_cast<const float2 *>(h.bc_table) + i);
+    a.step_size = s.x;
+    a.bc2_sqrt = s.y;
+    a.beta2 = (float)h.beta2;
+    a.eps = (float)h.eps;
+    a.w1 = (float)(1.0 - h.beta1);
+    a.w2 = (float)(1.0 - h.beta2);
+    return a;
+}
+
 __device__ __forceinline__ float clip_coef(const AdamHyper &h, double grad_norm_sq) {
     const float max_norm = (float)h.max_norm;
     const float total_norm = (float)sqrt(grad_norm_sq);

@@ -9,27 +9,26 @@
 // Why one kernel: a median ML-25M cluster batch has 2.2 k active rows and 7 k edges; as 16 launches
 // per step the epoch is bound by launch/drain latency and by dependent COLD misses (task -> index ->
 // row), ~185 us per step measured.  Here one CTA per SM stays resident for the whole run, phases are
-// separated by a device-wide barrier (~1 us), per-node metadata rides in the task descriptors
-// (deg_in / deg_out) so no O(N) array is touched, layer 1 gathers a PRE-SCALED table (no per-edge
-// normalisation gather), and while step b finishes the CTAs prefetch step b+1's descriptors, index
-// arrays and parameter rows into L2.
+// separated by device-wide barriers, per-node metadata rides in the task descriptors (deg_in /
+// deg_out) so no O(N) array is touched, layer 1 gathers a PRE-SCALED table (no per-edge normalisation
+// gather), and the next step's descriptors and index arrays are prefetched into L2.
 //
-// Phases of one step (K layers; `|` = grid barrier):
-//   A  replay pending Adam steps of the active rows, y0 = dis (.) e0, stamp rows as active          |
-//   B  forward layer 1  +  collect the distinct INACTIVE negatives of the step                      |
-//   C  replay pending Adam steps of those negatives  +  forward layers 2..K (barrier after each)    |
-//   E  BPR over user rows (loss, user-row gradient, negative-item gradient by vector atomics)       |
-//   F  BPR over item rows (positive-item gradient, owner computes); both write dis (.) G too        |
-//   G  backward layers 1..K (barrier after each); the last also forms the inactive negatives' grad  |
-//   J  clip + Adam step on the touched rows, restore the all-zero invariants, loss, prefetch b+1    |
-//
-// CTAs are split in two roles.  MAIN CTAs run phases B..J, separated by barriers among themselves.
-// HELPER CTAs (a quarter of the grid) spend that time bringing the NEXT step's user rows up to date
-// ("early replay"): a user row is touched once per epoch, so ~100 zero-gradient Adam steps -- IEEE
-// sqrt and two divisions per element and step -- are pending when its cluster comes up; that arithmetic
-// (the same amount dense Adam performs) would otherwise sit on the critical path of phase A.  A row that
-// the current step touches itself is skipped (phase J brings it to the same step).  Everybody meets
-// after phase A and at the end of the step.
+// Two CTA roles.  The replay of pending zero-gradient Adam steps is a long SEQUENTIAL chain per row (a
+// user row is touched once per epoch: ~100 steps, each with an IEEE sqrt and two divisions per element;
+// ~20 us for one warp) -- the same arithmetic dense Adam performs, but on the critical path if done when
+// the row is needed.  So:
+//   HELPER CTAs work one step AHEAD: during step b they prepare step b+1 -- stamp its active rows,
+//     collect its distinct inactive negatives (the run's negatives are sampled up front), and bring all
+//     those rows up to date, except rows step b touches itself (phase J leaves them up to date).
+//   MAIN CTAs run the phases of step b, separated by barriers among themselves:
+//     A  y0 = dis (.) e0 for the active rows                                                    |
+//     B  forward layers 1..K (barrier after each; the last forms the layer mean and 1/||.||)    |
+//     E  BPR over user rows (loss, user-row gradient, negative-item gradient by vector atomics) |
+//     F  BPR over item rows (positive-item gradient, owner computes); both write dis (.) G too  |
+//     G  backward layers 1..K (barrier after each); the last also forms the inactive negatives' grad |
+//     J  clip + Adam step on the touched rows, restore the all-zero invariants, loss, prefetch
+//   Everybody meets at the end of the step.  Step 0 is prepared by all CTAs before the loop.
+// Stamp / list arrays are double-buffered by step parity so that preparing b+1 never disturbs b.
 //
 // Memory rules inside the kernel: everything another SM may have written earlier in the launch is read
 // with ld.global.cg (L2, the coherence point); __ldg only for data that is immutable for the whole
@@ -42,7 +41,16 @@
 namespace lgcn {
 namespace ep {
 
-constexpr int EP_WARPS = 16;
+#ifndef EP_GATHER_UNROLL
+#define EP_GATHER_UNROLL 8
+#endif
+#ifndef EP_BPR_A_UNROLL
+#define EP_BPR_A_UNROLL 2
+#endif
+#ifndef EP_BPR_B_UNROLL
+#define EP_BPR_B_UNROLL 4
+#endif
+constexpr int EP_WARPS = 8;        // two CTAs per SM: normally one MAIN and one HELPER
 constexpr int EP_THREADS = EP_WARPS * 32;
 
 struct StepDesc {
@@ -67,12 +75,15 @@ struct EpochArgs {
     int64_t *step;
     AdamHyper h;
     float *final_emb, *rnorm, *G, *grad, *work;
-    int32_t *neg_count, *neg_flag, *neg_list, *act_stamp;
+    int32_t *neg_count;
+    int32_t *act_stamp;  // [2][N]  step in which the node is active, by step parity
+    int32_t *neg_flag;   // [2][I]  step in which the item is an inactive negative
+    int32_t *neg_list;   // [2][I]  the distinct inactive negatives
     float *scratch;
     double *accum;       // [2][4], by step parity
     int32_t *counts;     // [2] length of neg_list, by step parity
-    unsigned *bar;       // [0]: arrivals of all CTAs, [32]: arrivals of the main CTAs (monotonic counters)
-    int num_helpers;     // CTAs [gridDim.x - num_helpers, gridDim.x) replay the next step's user rows
+    unsigned *bar;       // monotonic arrival counters: [0] all CTAs, [32] main CTAs, [64] helper CTAs
+    int num_helpers;     // CTAs [gridDim.x - num_helpers, gridDim.x) prepare the next step
     float bpr_coeff;
     long long *prof;     // optional [num_steps][16] globaltimer stamps at the phase boundaries (diagnostics)
 };
@@ -103,6 +114,32 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
     __syncthreads();
 }
 
+// for_each_edge (rowtask.cuh) with the 32-edge chunk loop left ROLLED: the persistent kernel holds every
+// phase's code at once, and sixteen inlined copies of each edge body made it 220 KB -- every phase then
+// started with instruction-cache misses.  Same traversal order, same arithmetic.
+template <class Item, int kUnroll, class Fetch, class Load, class Apply>
+__device__ __forceinline__ void for_each_edge_rolled(int begin, int end, int lane, Fetch fetch, Load load, Apply apply) {
+    const int half = lane >> 4;
+    Item mine = fetch(begin + lane < end ? begin + lane : -1);
+    for (int base = begin; base < end; base += 32) {
+        const int n = min(32, end - base);
+        const int nb = base + 32 + lane;
+        Item next = fetch(nb < end ? nb : -1);
+#pragma unroll 1
+        for (int j = 0; j < n; j += 2 * kUnroll) {
+            Item it[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                it[u] = mine.shfl(j + 2 * u + half);
+                load(u, it[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) apply(u, it[u]);
+        }
+        mine = next;
+    }
+}
+
 struct Tab {                        // mutable e0 = (user_w, item_w)
     float *user, *item;
     int num_users;
@@ -130,7 +167,7 @@ __device__ __noinline__ void gather_sum(const int32_t *__restrict__ nbr, const f
                                            float4 &acc) {
     const int l16 = lane & 15;
     const float4 *x4 = reinterpret_cast<const float4 *>(x);
-    for_each_edge<Nbr>(
+    for_each_edge_rolled<Nbr, EP_GATHER_UNROLL>(
         begin, end, lane,
         [&](int e) { Nbr it; it.nbr = e >= 0 ? __ldg(nbr + e) : -1; it.v = f4zero(); return it; },
         [&](int, Nbr &it) { if (it.nbr >= 0) it.v = ldcg4(x4 + (size_t)it.nbr * D4 + l16); },
@@ -197,9 +234,9 @@ __device__ __forceinline__ float4 replay_row(bool valid, int row, int lane, int 
         // iterations only chain through one fma each for p, m, v: unrolling lets the sqrt / division
         // sequences of neighbouring steps overlap
         const float4 zero = f4zero();
-#pragma unroll 4
+#pragma unroll 2
         for (int t = from + 1; t <= target; ++t) {
-            const AdamScalars a = adam_scalars(h, t);
+            const AdamScalars a = adam_scalars_tab(h, t);
             adam_vec(p4, m4, v4, zero, 1.0f, a);
         }
         *pp = p4; m[o] = m4; v[o] = v4;
@@ -208,37 +245,38 @@ __device__ __forceinline__ float4 replay_row(bool valid, int row, int lane, int 
     return p4;
 }
 
-// The three row sets whose pending zero-gradient steps are replayed, behind ONE copy of the (unrolled)
-// Adam loop:  RP_ACTIVE  the step's active rows (in-tasks, first part): -> target, y0 = dis (.) e0, stamp
-//             RP_AHEAD   the NEXT step's user rows, unless the current step (stamp) updates them itself
-//             RP_LIST    rows `offset + list[i]` (the distinct inactive negatives)
-enum { RP_ACTIVE = 0, RP_AHEAD = 1, RP_LIST = 2 };
+// Touched by the step with number `tp` (its stamps live in act_p / flag_p)?  Such a row is left alone by
+// whoever prepares the following step: phase J of step tp brings it to step tp itself.
+__device__ __forceinline__ bool touched_by(int row, int num_users, int tp, const int32_t *act_p, const int32_t *flag_p) {
+    if (!act_p) return false;
+    if (__ldcg(act_p + row) == tp) return true;
+    return row >= num_users && __ldcg(flag_p + row - num_users) == tp;
+}
+
+// Replay the pending zero-gradient steps of a row set up to step `target`, behind ONE copy of the
+// (unrolled) Adam loop.  RP_ACTIVE: the first-part in-tasks' rows, which are also stamped as active in
+// step target+1;  RP_LIST: rows num_users + list[i].  Rows touched by step `target` itself are skipped.
+enum { RP_ACTIVE = 0, RP_LIST = 1 };
 
 __device__ __noinline__ void replay_rows(int mode, const lgcn_task *__restrict__ tasks, const int32_t *list, int count,
-                                         int offset, int target, int stamp_now, Tab w, float4 *m, float4 *v,
-                                         int32_t *row_step, int32_t *act_stamp, float *y0, AdamHyper h, int gw, int nw,
-                                         int lane) {
+                                         int target, Tab w, float4 *m, float4 *v, int32_t *row_step, int32_t *act_next,
+                                         const int32_t *act_p, const int32_t *flag_p, AdamHyper h, int gw, int nw, int lane) {
     const int l16 = lane & 15, half = lane >> 4;
     for (int base = gw * 2; base < count; base += nw * 2) {
         const int i = base + half;
         bool valid = i < count;
-        int row = 0, din = 0;
+        int row = 0;
         if (valid) {
             if (mode == RP_LIST) {
-                row = offset + __ldcg(list + i);
+                row = w.num_users + __ldcg(list + i);
             } else {
-                const int4 ta = __ldg(reinterpret_cast<const int4 *>(tasks + i));
-                const int4 tc = __ldg(reinterpret_cast<const int4 *>(tasks + i) + 1);
-                row = ta.x; din = tc.z;
-                valid = tc.x == 0;                           // first part of a split row speaks for the row
-                if (mode == RP_AHEAD && valid) valid = __ldcg(act_stamp + row) != stamp_now;
+                row = __ldg(&tasks[i].row);
+                valid = __ldg(&tasks[i].part) == 0;          // first part of a split row speaks for the row
+                if (valid && l16 == 0) act_next[row] = target + 1;
             }
+            if (valid) valid = !touched_by(row, w.num_users, target, act_p, flag_p);
         }
-        const float4 p4 = replay_row(valid, row, lane, target, w, m, v, row_step, h);
-        if (mode == RP_ACTIVE && valid) {
-            reinterpret_cast<float4 *>(y0)[(size_t)row * D4 + l16] = f4scale(dis_of(din), p4);
-            if (l16 == 0) act_stamp[row] = stamp_now;
-        }
+        replay_row(valid, row, lane, target, w, m, v, row_step, h);
     }
 }
 
@@ -297,17 +335,17 @@ struct TripB {
     }
 };
 
-__global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a) {
+__global__ void __launch_bounds__(EP_THREADS, 2) epoch_kernel(const EpochArgs a) {
     const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
     const int gw_all = blockIdx.x * EP_WARPS + (threadIdx.x >> 5), nw_all = gridDim.x * EP_WARPS;
-    const unsigned nblocks = gridDim.x, nmain = gridDim.x - a.num_helpers;
+    const unsigned nblocks = gridDim.x, nhelp = a.num_helpers, nmain = gridDim.x - a.num_helpers;
     const bool helper = blockIdx.x >= nmain;
     // main CTAs index their work among themselves; helpers among themselves
     const int gw = helper ? gw_all - (int)nmain * EP_WARPS : gw_all;
-    const int nw = helper ? a.num_helpers * EP_WARPS : (int)nmain * EP_WARPS;
+    const int nw = helper ? (int)nhelp * EP_WARPS : (int)nmain * EP_WARPS;
     const int gtid = blockIdx.x * EP_THREADS + threadIdx.x, nthreads = (int)nmain * EP_THREADS;
-    unsigned tgt_all = 0, tgt_main = 0;
-    unsigned *const bar_all = a.bar, *const bar_main = a.bar + 32;
+    unsigned tgt_all = 0, tgt_main = 0, tgt_help = 0;
+    unsigned *const bar_all = a.bar, *const bar_main = a.bar + 32, *const bar_help = a.bar + 64;
     const int K = a.K, U = a.num_users;
     const size_t n = (size_t)a.num_users + (size_t)a.num_items;
     const Tab w{a.user_w, a.item_w, U};
@@ -317,6 +355,34 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
     float4 *const G4 = reinterpret_cast<float4 *>(a.G);
     const float4 *const F4 = reinterpret_cast<const float4 *>(a.final_emb);
     const long long t0 = *a.step;                           // only rewritten after the first barrier of a step
+
+    // Prepare step s (number ts = t0+1+s): stamp its active rows, list its distinct inactive negatives, bring
+    // both row sets to step ts-1.  Rows touched by the previous step are skipped (has_prev).  Executed by the
+    // warps (pgw of pnw) of `pcount` CTAs that synchronise on `pbar`.
+    auto prepare = [&](int s_, int pgw, int pnw, unsigned *pbar, unsigned &ptgt, unsigned pcount) {
+        const StepDesc sd = a.steps[s_];
+        const int ts = (int)(t0 + 1 + s_), par = s_ & 1;
+        int32_t *act_s = a.act_stamp + (size_t)par * n, *flag_s = a.neg_flag + (size_t)par * a.num_items;
+        int32_t *list_s = a.neg_list + (size_t)par * a.num_items, *cnt_s = a.counts + par;
+        const int32_t *act_p = s_ > 0 ? a.act_stamp + (size_t)(par ^ 1) * n : nullptr;
+        const int32_t *flag_p = s_ > 0 ? a.neg_flag + (size_t)(par ^ 1) * a.num_items : nullptr;
+        if (pgw == 0 && lane == 0) *cnt_s = 0;
+        replay_rows(RP_ACTIVE, sd.in_tasks, nullptr, sd.n_in_tasks, ts - 1, w, a.m, a.v, a.row_step, act_s, act_p, flag_p, a.h,
+                    pgw, pnw, lane);
+        grid_barrier(pbar, ptgt, pcount);
+        for (long long base = (long long)pgw * 32; base < sd.P; base += (long long)pnw * 32) {
+            const long long tt = base + lane;
+            if (tt < sd.P) {
+                const int i = (int)__ldg(sd.neg + tt);
+                if (__ldcg(act_s + U + i) != ts && atomicExch(flag_s + i, ts) != ts) list_s[atomicAdd(cnt_s, 1)] = i;
+            }
+        }
+        grid_barrier(pbar, ptgt, pcount);
+        replay_rows(RP_LIST, nullptr, list_s, __ldcg(cnt_s), ts - 1, w, a.m, a.v, a.row_step, nullptr, act_p, flag_p, a.h, pgw,
+                    pnw, lane);
+    };
+    prepare(0, gw_all, nw_all, bar_all, tgt_all, nblocks);
+    grid_barrier(bar_all, tgt_all, nblocks);
 
     for (int b = 0; b < a.num_steps; ++b) {
         const StepDesc d = a.steps[b];
@@ -328,37 +394,31 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
         int ps = 0;
         stamp(a.prof, b, ps, gtid);
 
-        // ---- A: active rows -> step t-1, y0 = dis (.) e0, stamp ---------------------------------
-        if (gtid == 0) {
-            double *nx = a.accum + ((b + 1) & 1) * 4;
-            nx[0] = 0.0; nx[1] = 0.0; nx[2] = 0.0; nx[3] = 0.0;
-            a.counts[(b + 1) & 1] = 0;
-        }
-        replay_rows(RP_ACTIVE, d.in_tasks, nullptr, d.n_in_tasks, 0, t - 1, t, w, a.m, a.v, a.row_step, a.act_stamp, y0, a.h,
-                    gw_all, nw_all, lane);
-        grid_barrier(bar_all, tgt_all, nblocks);
-        stamp(a.prof, b, ps, gtid);
+        const int par = b & 1;
+        const int32_t *const act_cur = a.act_stamp + (size_t)par * n;
+        const int32_t *const list_cur = a.neg_list + (size_t)par * a.num_items;
 
         if (helper) {
-            // ---- early replay: the next step's user rows -> step t (skipping rows this step updates itself)
-            if (b + 1 < a.num_steps) {
-                const StepDesc nx = a.steps[b + 1];
-                replay_rows(RP_AHEAD, nx.in_tasks, nullptr, nx.n_in_user_tasks, 0, t, t, w, a.m, a.v, a.row_step, a.act_stamp,
-                            nullptr, a.h, gw, nw, lane);
-            }
+            if (b + 1 < a.num_steps) prepare(b + 1, gw, nw, bar_help, tgt_help, nhelp);
             grid_barrier(bar_all, tgt_all, nblocks);     // end of the step
             continue;
         }
 
-        // ---- B: distinct inactive negatives  +  forward layer 1 --------------------------------
-        for (long long base = (long long)gw * 32; base < d.P; base += (long long)nw * 32) {
-            const long long tt = base + lane;
-            if (tt < d.P) {
-                const int i = (int)__ldg(d.neg + tt);
-                if (__ldcg(a.act_stamp + U + i) != t && atomicExch(a.neg_flag + i, t) != t)
-                    a.neg_list[atomicAdd(cnt_cur, 1)] = i;
-            }
+        // ---- A: y0 = dis (.) e0 for the active rows (already at step t-1) ------------------------
+        if (gtid == 0) {
+            double *nx = a.accum + ((b + 1) & 1) * 4;
+            nx[0] = 0.0; nx[1] = 0.0; nx[2] = 0.0; nx[3] = 0.0;
         }
+        for (int ti = gw * 2 + half; ti < d.n_in_tasks; ti += nw * 2) {
+            const int4 ta = __ldg(reinterpret_cast<const int4 *>(d.in_tasks + ti));
+            const int4 tc = __ldg(reinterpret_cast<const int4 *>(d.in_tasks + ti) + 1);
+            if (tc.x == 0)
+                reinterpret_cast<float4 *>(y0)[(size_t)ta.x * D4 + l16] = f4scale(dis_of(tc.z), ldcg4(w.row4(ta.x) + l16));
+        }
+        grid_barrier(bar_main, tgt_main, nmain);
+        stamp(a.prof, b, ps, gtid);
+
+        // ---- B: forward layers 1..K --------------------------------------------------------------
         auto fwd_layer = [&](int k) {
             const float *src = k == 1 ? y0 : a.work + (size_t)(k - 2) * n * D;
             float *dst = a.work + (size_t)(k - 1) * n * D;
@@ -383,13 +443,8 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
                           }
                       });
         };
-        // ---- C: negatives -> step t-1 (any time between the first barrier below and phase E) ------
-        //      K == 1 has no second forward layer to share a phase with: one extra round of the loop
-        for (int k = 1; k <= (K == 1 ? 2 : K); ++k) {
-            if (k == 2)
-                replay_rows(RP_LIST, nullptr, a.neg_list, __ldcg(cnt_cur), U, t - 1, t, w, a.m, a.v, a.row_step, a.act_stamp,
-                            nullptr, a.h, gw, nw, lane);
-            if (k <= K) fwd_layer(k);
+        for (int k = 1; k <= K; ++k) {
+            fwd_layer(k);
             grid_barrier(bar_main, tgt_main, nmain);
             stamp(a.prof, b, ps, gtid);
         }
@@ -401,7 +456,7 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
                       const float ru = __ldcg(a.rnorm + row);
                       const float4 fu = f4scale(ru, ldcg4(F4 + (size_t)row * D4 + l16));
                       float loss = 0.f;
-                      for_each_edge<TripA, 4>(
+                      for_each_edge_rolled<TripA, EP_BPR_A_UNROLL>(
                           begin, end, lane,
                           [&](int e) {
                               TripA it;
@@ -412,7 +467,7 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
                                   it.t = __ldg(d.out_trip + e);
                                   it.ng = (int)__ldg(d.neg + it.t) + U;
                                   it.rp = __ldcg(a.rnorm + it.dst);
-                                  if (__ldcg(a.act_stamp + it.ng) != t) it.rn = -1.f;      // inactive: formed below
+                                  if (__ldcg(act_cur + it.ng) != t) it.rn = -1.f;      // inactive: formed below
                                   else it.rn = __ldcg(a.rnorm + it.ng);
                               }
                               return it;
@@ -469,7 +524,7 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
         // ---- F: BPR over item rows -------------------------------------------------------------
         run_tasks(d.in_tasks, d.n_in_user_tasks, d.n_in_tasks, d.partials, d.slot_counters, gw, nw, lane,
                   [&](int, int begin, int end, float4 &acc, float &sc) {
-                      for_each_edge<TripB, UNROLL>(
+                      for_each_edge_rolled<TripB, EP_BPR_B_UNROLL>(
                           begin, end, lane,
                           [&](int e) {
                               TripB it;
@@ -537,7 +592,7 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
                     float4 g = f4zero();
                     float reg = 0.f;
                     if (idx < cnt) {
-                        const int item = __ldcg(a.neg_list + idx), row = U + item;
+                        const int item = __ldcg(list_cur + idx), row = U + item;
                         g = f4scale(c0, ldcg4(G4 + (size_t)row * D4 + l16));
                         G4[(size_t)row * D4 + l16] = f4zero();
                         const int c = __ldcg(a.neg_count + item);
@@ -560,7 +615,7 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
 
         // ---- J: clip + Adam step t on the touched rows, loss, prefetch the next step -------------
         {
-            const AdamScalars as = adam_scalars(a.h, t);
+            const AdamScalars as = adam_scalars_tab(a.h, t);
             const float clip = clip_coef(a.h, __ldcg(acc_cur + 2));
             const float4 *gr = reinterpret_cast<const float4 *>(a.grad);
             for (int base = gw * 2; base < d.n_in_tasks; base += nw * 2) {
@@ -573,7 +628,7 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
             }
             const int cnt = __ldcg(cnt_cur);
             for (int idx = gw * 2 + half; idx < cnt; idx += nw * 2)
-                adam_row(U + __ldcg(a.neg_list + idx), lane, t, w, a.m, a.v, gr, G4, a.row_step, a.neg_count, clip, as);
+                adam_row(U + __ldcg(list_cur + idx), lane, t, w, a.m, a.v, gr, G4, a.row_step, a.neg_count, clip, as);
             if (gtid == 0) {
                 const double p = (double)d.P;
                 d.loss_out[0] = (float)(-__ldcg(acc_cur + 0) / (10.0 * p) + (double)a.bpr_coeff * __ldcg(acc_cur + 1) / (64.0 * p));
@@ -588,14 +643,6 @@ __global__ void __launch_bounds__(EP_THREADS, 1) epoch_kernel(const EpochArgs a)
                 prefetch_range(nx.in_trip, 4 * (size_t)nx.num_edges, gtid, nthreads);
                 prefetch_range(nx.out_trip, 4 * (size_t)nx.num_edges, gtid, nthreads);
                 prefetch_range(nx.neg, 8 * (size_t)nx.P, gtid, nthreads);
-                // parameter / moment rows of the next step's active nodes (one 128-byte line per lane pair)
-                for (int ti = gtid >> 1; ti < nx.n_in_tasks; ti += nthreads >> 1) {
-                    const int row = __ldg(&nx.in_tasks[ti].row);
-                    const size_t o = (size_t)row * D + (size_t)(gtid & 1) * 32;
-                    prefetch_l2(reinterpret_cast<const float *>(w.row4(row)) + (gtid & 1) * 32);
-                    prefetch_l2(reinterpret_cast<const float *>(a.m) + o);
-                    prefetch_l2(reinterpret_cast<const float *>(a.v) + o);
-                }
             }
         }
         grid_barrier(bar_all, tgt_all, nblocks);
@@ -625,10 +672,10 @@ extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_ste
                  "train_steps_sparse: null argument");
     LGCN_REQUIRE(num_steps >= 1 && num_steps < (1 << 24), LGCN_E_INVALID, "train_steps_sparse: %lld steps", (long long)num_steps);
     LGCN_REQUIRE(K >= 1 && K <= 4, LGCN_E_INVALID, "train_steps_sparse: num_layers %d outside [1,4]", K);
-    LGCN_REQUIRE(opt->row_step && opt->m && opt->v && opt->step && opt->bc_table, LGCN_E_INVALID,
-                 "train_steps_sparse: optimiser state (row_step, m, v, step, bc_table) missing");
+    LGCN_REQUIRE(opt->row_step && opt->m && opt->v && opt->step && opt->bc_table && opt->bc_len > num_steps, LGCN_E_INVALID,
+                 "train_steps_sparse: optimiser state (row_step, m, v, step, bc_table covering the run) missing");
     LGCN_REQUIRE(buf->final_emb && buf->rnorm && buf->grad_final && buf->grad_e0 && buf->neg_count && buf->trip_scratch &&
-                 buf->neg_flag && buf->neg_list && buf->act_stamp, LGCN_E_INVALID, "train_steps_sparse: step buffers missing");
+                 buf->act_stamp, LGCN_E_INVALID, "train_steps_sparse: step buffers missing");
     LGCN_REQUIRE(workspace_bytes >= lgcn_train_steps_workspace_bytes(num_steps), LGCN_E_WORKSPACE,
                  "train_steps_sparse: workspace %zu < %zu", workspace_bytes, lgcn_train_steps_workspace_bytes(num_steps));
     const int N = graphs[0].num_nodes, U = graphs[0].num_users;
@@ -667,9 +714,10 @@ extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_ste
     a.m = reinterpret_cast<float4 *>(opt->m); a.v = reinterpret_cast<float4 *>(opt->v);
     a.row_step = opt->row_step; a.step = opt->step; a.h = make_hyper(opt);
     a.final_emb = buf->final_emb; a.rnorm = buf->rnorm; a.G = buf->grad_final; a.grad = buf->grad_e0; a.work = buf->work;
-    a.neg_count = buf->neg_count; a.neg_flag = buf->neg_flag; a.neg_list = buf->neg_list; a.act_stamp = buf->act_stamp;
+    a.neg_count = buf->neg_count;
+    a.act_stamp = buf->act_stamp; a.neg_flag = buf->act_stamp + 2 * (size_t)N; a.neg_list = a.neg_flag + 2 * (size_t)(N - U);
     a.scratch = buf->trip_scratch;
-    a.accum = (double *)state; a.counts = (int32_t *)(state + 64); a.bar = (unsigned *)(state + 128);   // bar[32] = state + 256
+    a.accum = (double *)state; a.counts = (int32_t *)(state + 64); a.bar = (unsigned *)(state + 128);   // [0], [32], [64]: 128 bytes apart
     a.bpr_coeff = bpr_coeff;
     static const bool want_prof = getenv("LGCN_EPOCH_PROF") != nullptr;   // tools/epoch_breakdown.py
     a.prof = want_prof ? (long long *)(state + 512) : nullptr;
@@ -683,10 +731,11 @@ extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_ste
         LGCN_REQUIRE(coop, LGCN_E_CUDA, "train_steps_sparse: device does not support cooperative launches");
         LGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epoch_kernel, EP_THREADS, 0));
         LGCN_REQUIRE(per_sm >= 1, LGCN_E_CUDA, "train_steps_sparse: kernel does not fit on an SM");
-        grid = sms;
+        grid = sms * (per_sm >= 2 ? 2 : 1);
     }
     static const int helpers_env = getenv("LGCN_EPOCH_HELPERS") ? atoi(getenv("LGCN_EPOCH_HELPERS")) : -1;   // tuning aid
-    a.num_helpers = num_steps > 1 ? (helpers_env >= 0 ? helpers_env : 0) : 0;
+    a.num_helpers = num_steps > 1 ? (helpers_env >= 1 ? helpers_env : grid / 2) : 0;
+    if (num_steps > 1 && a.num_helpers < 1) a.num_helpers = 1;
     if (a.num_helpers > grid - 1) a.num_helpers = grid - 1;
     void *params[] = {(void *)&a};
     LGCN_CUDA(cudaLaunchCooperativeKernel((const void *)epoch_kernel, dim3(grid), dim3(EP_THREADS), params, 0, st));

@@ -55,10 +55,10 @@ if os.environ.get("LGCN_EPOCH_PROF"):
     L = _lib.lib()
     nb = len(parts)
     ws = opt.buffers.steps_ws
-    desc_bytes = L.lgcn_train_steps_workspace_bytes(nb) - 256 - 128 * nb
-    prof = ws[desc_bytes + 256: desc_bytes + 256 + 128 * nb].view(torch.int64).view(nb, 16).cpu().numpy()
+    desc_bytes = L.lgcn_train_steps_workspace_bytes(nb) - 512 - 128 * nb
+    prof = ws[desc_bytes + 512: desc_bytes + 512 + 128 * nb].view(torch.int64).view(nb, 16).cpu().numpy()
     dur = np.diff(prof[:, :11], axis=1) / 1e3
-    names = ["A replay+prescale", "B fwd1+mark", "C fwd2+negreplay", "fwd3", "E bpr users", "F bpr items", "bwd1", "bwd2",
+    names = ["A prescale", "fwd1", "fwd2", "fwd3", "E bpr users", "F bpr items", "bwd1", "bwd2",
              "bwd3+negs", "J adam+prefetch"]
     print("per-phase us over %d steps (median / mean / max):" % nb)
     for i, nm in enumerate(names):
