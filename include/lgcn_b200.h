@@ -349,7 +349,7 @@ int lgcn_score_topk(const float *user_emb, const float *item_emb, int64_t num_it
                     void *stream);
 
 /* Same with an explicit kernel choice: LGCN_SCORE_TENSOR = tcgen05 TF32 MMA with a 3-term hi/lo
- * operand split (fp32-level accuracy), accumulator in TMEM, k <= 64; LGCN_SCORE_FFMA = fp32 FFMA tiles,
+ * operand split (fp32-level accuracy), accumulator in TMEM, k <= 32; LGCN_SCORE_FFMA = fp32 FFMA tiles,
  * k <= 128; LGCN_SCORE_AUTO picks the tensor-core kernel whenever k allows. */
 #define LGCN_SCORE_AUTO 0
 #define LGCN_SCORE_FFMA 1
@@ -359,6 +359,15 @@ int lgcn_score_topk_ex(const float *user_emb, const float *item_emb, int64_t num
                        int64_t u_begin, int64_t u_end, int normalize, const int64_t *excl_ptr,
                        const int32_t *excl_idx, int k, int32_t *topk_idx, float *topk_val, int algo,
                        void *stream);
+
+/* ---- diagnostics ------------------------------------------------------------------------------ */
+
+/* Gathers ctas * 16 * rows_per_halfwarp pseudo-random 256-byte rows of table [nrows,64] with the
+ * propagation kernels' access shape and nothing else (no index array, no dependent address): the
+ * measured ceiling their gather rate is quoted against (tools/gather_peak.py, bench.py).  sink:
+ * ctas * 16 floats, never written in practice. */
+int lgcn_probe_gather(const float *table, int64_t nrows, int ctas, int rows_per_halfwarp, float *sink,
+                      void *stream);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,10 @@ namespace ep {
 #ifndef EP_BPR_B_UNROLL
 #define EP_BPR_B_UNROLL 4
 #endif
-constexpr int EP_WARPS = 8;        // two CTAs per SM: normally one MAIN and one HELPER
+#ifndef EP_CTAS_PER_SM
+#define EP_CTAS_PER_SM 3
+#endif
+constexpr int EP_WARPS = 8;        // EP_CTAS_PER_SM CTAs per SM: one of them a HELPER, the others MAIN
 constexpr int EP_THREADS = EP_WARPS * 32;
 
 struct StepDesc {
@@ -335,7 +338,7 @@ struct TripB {
     }
 };
 
-__global__ void __launch_bounds__(EP_THREADS, 2) epoch_kernel(const EpochArgs a) {
+__global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const EpochArgs a) {
     const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
     const int gw_all = blockIdx.x * EP_WARPS + (threadIdx.x >> 5), nw_all = gridDim.x * EP_WARPS;
     const unsigned nblocks = gridDim.x, nhelp = a.num_helpers, nmain = gridDim.x - a.num_helpers;
@@ -731,10 +734,10 @@ extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_ste
         LGCN_REQUIRE(coop, LGCN_E_CUDA, "train_steps_sparse: device does not support cooperative launches");
         LGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epoch_kernel, EP_THREADS, 0));
         LGCN_REQUIRE(per_sm >= 1, LGCN_E_CUDA, "train_steps_sparse: kernel does not fit on an SM");
-        grid = sms * (per_sm >= 2 ? 2 : 1);
+        grid = sms * (per_sm >= EP_CTAS_PER_SM ? EP_CTAS_PER_SM : per_sm);
     }
     static const int helpers_env = getenv("LGCN_EPOCH_HELPERS") ? atoi(getenv("LGCN_EPOCH_HELPERS")) : -1;   // tuning aid
-    a.num_helpers = num_steps > 1 ? (helpers_env >= 1 ? helpers_env : grid / 2) : 0;
+    a.num_helpers = num_steps > 1 ? (helpers_env >= 1 ? helpers_env : (grid * 9) / 20) : 0;
     if (num_steps > 1 && a.num_helpers < 1) a.num_helpers = 1;
     if (a.num_helpers > grid - 1) a.num_helpers = grid - 1;
     void *params[] = {(void *)&a};

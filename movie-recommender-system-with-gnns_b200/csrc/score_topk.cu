@@ -283,8 +283,8 @@ extern "C" int lgcn_score_topk_ex(const float *user_emb, const float *item_emb, 
     cudaStream_t st = (cudaStream_t)stream;
     LGCN_REQUIRE(algo == LGCN_SCORE_AUTO || algo == LGCN_SCORE_FFMA || algo == LGCN_SCORE_TENSOR, LGCN_E_INVALID,
                  "score_topk: unknown algo %d", algo);
-    LGCN_REQUIRE(algo != LGCN_SCORE_TENSOR || k <= 64, LGCN_E_INVALID, "score_topk: the tensor-core kernel keeps k <= 64");
-    if (algo == LGCN_SCORE_TENSOR || (algo == LGCN_SCORE_AUTO && k <= 64 && LGCN_SCORE_AUTO_USES_TENSOR))
+    LGCN_REQUIRE(algo != LGCN_SCORE_TENSOR || k <= 32, LGCN_E_INVALID, "score_topk: the tensor-core kernel keeps k <= 32");
+    if (algo == LGCN_SCORE_TENSOR || (algo == LGCN_SCORE_AUTO && k <= 32 && LGCN_SCORE_AUTO_USES_TENSOR))
         return score_topk_tc_impl(user_emb, item_emb, num_items, u_begin, u_end, normalize, excl_ptr, excl_idx, k, topk_idx,
                                   topk_val, st);
     if (k <= 32) return launch_topk<1>(user_emb, item_emb, num_items, u_begin, u_end, normalize, excl_ptr, excl_idx, k, topk_idx, topk_val, st);

@@ -104,8 +104,8 @@ def _check_topk(ids, vals, oids, ovals, tol):
 @pytest.mark.parametrize("shape,k,normalize", [("tiny", 20, True), ("ml100k", 20, True), ("ml100k", 10, False),
                                                ("ml100k", 100, True), ("ml100k", 50, True), ("ml1m", 20, True)])
 def test_score_topk_vs_bruteforce_oracle(shape, k, normalize, algo):
-    if algo == rec.SCORE_TENSOR and k > 64:
-        pytest.skip("tensor-core kernel keeps k <= 64")
+    if algo == rec.SCORE_TENSOR and k > 32:
+        pytest.skip("tensor-core kernel keeps k <= 32")
     g = synthetic.make_graph(shape, seed=0)
     u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 5)
     train = g.edges("train")
