@@ -358,7 +358,11 @@ int lgcn_score_topk(const float *user_emb, const float *item_emb, int64_t num_it
 int lgcn_score_topk_ex(const float *user_emb, const float *item_emb, int64_t num_items,
                        int64_t u_begin, int64_t u_end, int normalize, const int64_t *excl_ptr,
                        const int32_t *excl_idx, int k, int32_t *topk_idx, float *topk_val, int algo,
-                       void *stream);
+                       void *workspace, size_t workspace_bytes, void *stream);
+/* Optional workspace of the tensor-core kernel (device, 128-byte aligned): with it the item table is
+ * normalised and split once into ready-made shared-memory tile images that the kernel fetches with TMA
+ * bulk copies; without it (NULL) every CTA prepares the item tiles itself (slower). */
+size_t lgcn_score_topk_workspace_bytes(int64_t num_items);
 
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 

@@ -30,6 +30,7 @@ EXPORTS = [
     "lgcn_bpr_fwd_bwd_range", "lgcn_clip_adam_rows", "lgcn_train_step_sparse", "lgcn_adam_flush",
     "lgcn_peer_barrier", "lgcn_score_topk_ex", "lgcn_graph_batched_sizes", "lgcn_graph_build_batched",
     "lgcn_train_steps_workspace_bytes", "lgcn_train_steps_sparse", "lgcn_probe_gather",
+    "lgcn_score_topk_workspace_bytes",
 ]
 
 
@@ -120,7 +121,9 @@ def lib():
     L.lgcn_score_topk.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int,
                                   c_void_p, c_void_p, c_void_p]
     L.lgcn_score_topk_ex.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int,
-                                     c_void_p, c_void_p, c_int, c_void_p]
+                                     c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]
+    L.lgcn_score_topk_workspace_bytes.argtypes = [c_int64]
+    L.lgcn_score_topk_workspace_bytes.restype = c_size_t
     L.lgcn_spmm.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int, c_void_p]
     L.lgcn_bpr_rows.argtypes = [c_void_p] * 6 + [c_int64, c_float, c_void_p, c_void_p, c_void_p] + [c_void_p] * 6 + [c_void_p]
     L.lgcn_prescale.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(CPeers), c_void_p]
@@ -145,7 +148,8 @@ def lib():
                                           POINTER(CStepBuffers), c_void_p, c_void_p, c_size_t, c_void_p]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("lgcn_last_error", "lgcn_cluster_extract_workspace_bytes", "lgcn_train_steps_workspace_bytes"):
+        if name not in ("lgcn_last_error", "lgcn_cluster_extract_workspace_bytes", "lgcn_train_steps_workspace_bytes",
+                        "lgcn_score_topk_workspace_bytes"):
             fn.restype = c_int
     _lib = L
     return L

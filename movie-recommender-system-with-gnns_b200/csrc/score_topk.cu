@@ -260,7 +260,8 @@ static int launch_topk(const float *ue, const float *ie, int64_t I, int64_t ub, 
 }
 
 int score_topk_tc_impl(const float *, const float *, int64_t, int64_t, int64_t, int, const int64_t *, const int32_t *,
-                       int, int32_t *, float *, cudaStream_t);
+                       int, int32_t *, float *, void *, size_t, cudaStream_t);
+size_t score_topk_tc_workspace_bytes(int64_t);
 
 }  // namespace lgcn
 
@@ -268,12 +269,17 @@ extern "C" int lgcn_score_topk(const float *user_emb, const float *item_emb, int
                                int64_t u_end, int normalize, const int64_t *excl_ptr, const int32_t *excl_idx,
                                int k, int32_t *topk_idx, float *topk_val, void *stream) {
     return lgcn_score_topk_ex(user_emb, item_emb, num_items, u_begin, u_end, normalize, excl_ptr, excl_idx, k,
-                              topk_idx, topk_val, LGCN_SCORE_AUTO, stream);
+                              topk_idx, topk_val, LGCN_SCORE_AUTO, nullptr, 0, stream);
+}
+
+extern "C" size_t lgcn_score_topk_workspace_bytes(int64_t num_items) {
+    return num_items > 0 ? lgcn::score_topk_tc_workspace_bytes(num_items) : 0;
 }
 
 extern "C" int lgcn_score_topk_ex(const float *user_emb, const float *item_emb, int64_t num_items, int64_t u_begin,
                                   int64_t u_end, int normalize, const int64_t *excl_ptr, const int32_t *excl_idx,
-                                  int k, int32_t *topk_idx, float *topk_val, int algo, void *stream) {
+                                  int k, int32_t *topk_idx, float *topk_val, int algo, void *workspace,
+                                  size_t workspace_bytes, void *stream) {
     using namespace lgcn;
     LGCN_REQUIRE(user_emb && item_emb && topk_idx && topk_val, LGCN_E_INVALID, "score_topk: null argument");
     LGCN_REQUIRE(k >= 1 && k <= 128, LGCN_E_INVALID, "score_topk: k=%d outside [1,128]", k);
@@ -286,7 +292,7 @@ extern "C" int lgcn_score_topk_ex(const float *user_emb, const float *item_emb, 
     LGCN_REQUIRE(algo != LGCN_SCORE_TENSOR || k <= 32, LGCN_E_INVALID, "score_topk: the tensor-core kernel keeps k <= 32");
     if (algo == LGCN_SCORE_TENSOR || (algo == LGCN_SCORE_AUTO && k <= 32 && LGCN_SCORE_AUTO_USES_TENSOR))
         return score_topk_tc_impl(user_emb, item_emb, num_items, u_begin, u_end, normalize, excl_ptr, excl_idx, k, topk_idx,
-                                  topk_val, st);
+                                  topk_val, workspace, workspace_bytes, st);
     if (k <= 32) return launch_topk<1>(user_emb, item_emb, num_items, u_begin, u_end, normalize, excl_ptr, excl_idx, k, topk_idx, topk_val, st);
     if (k <= 64) return launch_topk<2>(user_emb, item_emb, num_items, u_begin, u_end, normalize, excl_ptr, excl_idx, k, topk_idx, topk_val, st);
     return launch_topk<4>(user_emb, item_emb, num_items, u_begin, u_end, normalize, excl_ptr, excl_idx, k, topk_idx, topk_val, st);

@@ -23,9 +23,16 @@
 //              (ncu: those were 43 % of the epilogue warps' samples and made them the bottleneck).
 //   warp  4    one elected thread issues 24 tcgen05.mma (8 K-steps x 3 split terms, M=128 N=64 K=8)
 //              per tile and commits to mbarriers
-//   warps 5-8  producers: gather 64 item rows, L2-normalise, split hi/lo, store in the UMMA K-major
-//              no-swizzle ("interleaved") core-matrix layout, fence.proxy.async, arrive
+//   warps 5-12 producers (two groups of four, one per stage): gather 64 item rows, L2-normalise, split
+//              hi/lo, store in the UMMA K-major no-swizzle ("interleaved") core-matrix layout,
+//              fence.proxy.async, arrive
 // Two shared-memory stages for B and two TMEM accumulator stages (2 x 64 columns) decouple the roles.
+//
+// PACKED variant (lgcn_score_topk_ex with a workspace): a pre-pass normalises and splits the item table
+// ONCE into the shared-memory image of every 64-item tile (hi tile, lo tile: 32 KB, back to back in global
+// memory), and the producer is a single thread issuing two 16 KB TMA bulk copies per tile
+// (cp.async.bulk ... mbarrier::complete_tx) -- instead of every CTA re-normalising all items with eight
+// warps whose dependent L2 gathers set a floor of ~1900 cycles per tile (round-1 ncu / timing experiments).
 #include "common.cuh"
 #include <limits.h>
 #include <stdint.h>
@@ -39,7 +46,9 @@ constexpr int GROUP_BYTES = 2048;                 // 8 rows x 256 B: 16 core mat
 constexpr int A_BYTES = (BM / 8) * GROUP_BYTES;   // 32 KB per split half
 constexpr int B_BYTES = (BN / 8) * GROUP_BYTES;   // 16 KB per split half
 constexpr int NUM_EPI = 128, NUM_PROD = 128;
-constexpr int THREADS = NUM_EPI + 32 + NUM_PROD;  // 288
+constexpr int PROD_GROUPS = 2;                    // producer group g fills stage g for tiles t = g (mod 2)
+constexpr int THREADS = NUM_EPI + 32 + PROD_GROUPS * NUM_PROD;  // 416
+constexpr int THREADS_PACKED = NUM_EPI + 32 + 32;  // 192: epilogue, MMA issuer, TMA issuer
 constexpr int TMEM_COLS = 128;                    // 2 accumulator stages x 64 fp32 columns
 constexpr int KMAX = 32;                          // k <= 32: the buffer keeps k + 64 candidates
 constexpr int CAND = KMAX + 64;
@@ -130,8 +139,18 @@ struct __align__(16) Smem {
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
-score_topk_tc_kernel(const float *__restrict__ user_emb, const float *__restrict__ item_emb, int64_t num_items,
+// The shared-memory image of item tile t (rows [64 t, 64 t + 64)): normalised, split, core-matrix layout.
+__global__ void __launch_bounds__(256)
+pack_items_kernel(const float *__restrict__ item_emb, int64_t num_items, int normalize, unsigned char *__restrict__ packed) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;      // warp = 8-row group of the tile
+    unsigned char *tile = packed + (size_t)blockIdx.x * (2 * B_BYTES);
+    load_rows8(item_emb, (int64_t)blockIdx.x * BN, num_items, normalize != 0, tile, tile + B_BYTES, warp, lane);
+}
+
+template <bool kPacked>
+__global__ void __launch_bounds__(kPacked ? THREADS_PACKED : THREADS, 1)
+score_topk_tc_kernel(const float *__restrict__ user_emb, const float *__restrict__ item_emb,
+                     const unsigned char *__restrict__ packed, int64_t num_items,
                      int64_t u_begin, int64_t u_end, int normalize, const int64_t *__restrict__ excl_ptr,
                      const int32_t *__restrict__ excl_idx, int k, int32_t *__restrict__ topk_idx,
                      float *__restrict__ topk_val) {
@@ -140,13 +159,17 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const float *__restrict
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t u0 = u_begin + (int64_t)blockIdx.x * BM;
     const int num_tiles = (int)((num_items + BN - 1) / BN);
+    // Every CTA walks ALL item tiles; staggered starting points keep the 148 resident CTAs from asking the
+    // same L2 lines for the same tile at the same moment (iteration i handles tile (tile0 + i) mod num_tiles).
+    const int tile0 = (int)(((long long)blockIdx.x * 61) % num_tiles);
+#define TILE_OF(i) ((tile0 + (i)) < num_tiles ? (tile0 + (i)) : (tile0 + (i)) - num_tiles)
 
     // ---- one-time setup ------------------------------------------------------------------------
-    for (int grp = warp; grp < BM / 8; grp += THREADS / 32)
+    for (int grp = warp; grp < BM / 8; grp += (int)(blockDim.x >> 5))
         load_rows8(user_emb, u0, u_end, normalize != 0, S.a_hi, S.a_lo, grp, lane);
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&S.full[s], NUM_PROD);
+            mbar_init(&S.full[s], kPacked ? 1 : NUM_PROD);
             mbar_init(&S.empty[s], 1);
             mbar_init(&S.tfull[s], 1);
             mbar_init(&S.tempty[s], NUM_EPI / 32);
@@ -164,13 +187,30 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const float *__restrict
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = S.tmem_base;
 
-    if (warp >= 5) {
+    if (kPacked && warp >= 5) {
+        // ===== TMA issuer: two 16 KB bulk copies per tile, completion counted in bytes on full[s] ==
+        if (warp == 5 && lane == 0) {
+            for (int t = 0; t < num_tiles; ++t) {
+                const int s = t & 1;
+                mbar_wait(&S.empty[s], ((t >> 1) & 1) ^ 1);
+                const unsigned char *src = packed + (size_t)TILE_OF(t) * (2 * B_BYTES);
+                const uint32_t bar = smem_u32(&S.full[s]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(2 * B_BYTES) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(S.b_hi[s])), "l"(src), "r"(B_BYTES), "r"(bar) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(S.b_lo[s])), "l"(src + B_BYTES), "r"(B_BYTES), "r"(bar) : "memory");
+            }
+        }
+    } else if (warp >= 5) {
         // ===== producers: item tiles -> shared memory (hi / lo halves) ============================
-        const int pw = warp - 5;
-        for (int t = 0; t < num_tiles; ++t) {
+        // two groups of four warps, one per shared-memory stage: a group has two tile periods to cover the
+        // L2 latency of its row gathers (with one group the loads were exposed: ncu, round 1)
+        const int pw = (warp - 5) & 3, grp = (warp - 5) >> 2;
+        for (int t = grp; t < num_tiles; t += PROD_GROUPS) {
             const int s = t & 1;
             mbar_wait(&S.empty[s], ((t >> 1) & 1) ^ 1);
-            const int64_t n0 = (int64_t)t * BN;
+            const int64_t n0 = (int64_t)TILE_OF(t) * BN;
 #pragma unroll
             for (int it = 0; it < 2; ++it)
                 load_rows8(item_emb, n0, num_items, normalize != 0, S.b_hi[s], S.b_lo[s], pw * 2 + it, lane);
@@ -205,7 +245,18 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const float *__restrict
         const int m = tid;                                     // 0..127
         const bool live = u0 + m < u_end;
         int64_t ex_cur = 0, ex_end = 0;
-        if (live && excl_ptr) { ex_cur = excl_ptr[u0 + m]; ex_end = excl_ptr[u0 + m + 1]; }
+        int64_t ex_begin = 0;
+        if (live && excl_ptr) {
+            ex_begin = excl_ptr[u0 + m];
+            ex_end = excl_ptr[u0 + m + 1];
+            int64_t lo = ex_begin, hi = ex_end;                // first excluded item at or after the first tile
+            const int64_t first = (int64_t)tile0 * BN;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (excl_idx[mid] < first) lo = mid + 1; else hi = mid;
+            }
+            ex_cur = lo;
+        }
         // next excluded item kept in a register: a tile without one costs a compare, not a global load
         int64_t ex_next = ex_cur < ex_end ? (int64_t)excl_idx[ex_cur] : INT64_MAX;
         // admission: a score enters the buffer iff it orders before (thr, thr_id) under (score desc, id asc);
@@ -329,7 +380,12 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const float *__restrict
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.tempty[s]);           // accumulator stage may be overwritten
-            const int64_t n0 = (int64_t)t * BN;
+            const int tile = TILE_OF(t);
+            const int64_t n0 = (int64_t)tile * BN;
+            if (tile == 0 && t > 0) {                           // wrapped around: back to the head of the exclusion row
+                ex_cur = ex_begin;
+                ex_next = ex_cur < ex_end ? (int64_t)excl_idx[ex_cur] : INT64_MAX;
+            }
             unsigned long long mask = 0ull;                     // train items of this user inside the tile
             while (ex_next < n0 + BN) {
                 if (ex_next >= n0) mask |= 1ull << (int)(ex_next - n0);
@@ -363,11 +419,24 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const float *__restrict
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         if (gm[g] >= thr) {
+                            // which of the 8 columns pass: a bit per column, then only the set bits are visited
+                            // (usually one lane, one bit) instead of eight predicated bodies
+                            const int c0 = 32 * h + 8 * g;
+                            unsigned pass = 0u;
 #pragma unroll
-                            for (int c = 32 * h + 8 * g; c < 32 * h + 8 * g + 8; ++c) {
-                                const float sc = __uint_as_float(r[c]) + 0.0f;      // -0 -> +0: one image per value
-                                const int id = (int)(n0 + c);
-                                if (sc >= thr && ((admissible >> c) & 1ull) && (sc > thr || id < thr_id)) {
+                            for (int j = 0; j < 8; ++j)
+                                pass |= (__uint_as_float(r[c0 + j]) >= thr ? 1u : 0u) << j;
+                            pass &= (unsigned)(admissible >> c0) & 0xffu;
+                            while (pass) {
+                                const int j = __ffs(pass) - 1;
+                                pass &= pass - 1;
+                                float sc = 0.f;
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    if (q == j) sc = __uint_as_float(r[c0 + q]);          // registers cannot be indexed
+                                sc += 0.0f;                                              // -0 -> +0: one image per value
+                                const int id = (int)(n0 + c0 + j);
+                                if (sc > thr || id < thr_id) {
                                     S.cand_v[cnt][m] = sc;
                                     S.cand_i[cnt][m] = id;
                                     ++cnt;
@@ -396,6 +465,7 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const float *__restrict
             }
         }
     }
+#undef TILE_OF
     // ---- teardown ------------------------------------------------------------------------------
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -408,13 +478,30 @@ score_topk_tc_kernel(const float *__restrict__ user_emb, const float *__restrict
 }  // namespace tc
 
 int score_topk_tc_impl(const float *ue, const float *ie, int64_t I, int64_t ub, int64_t uend, int normalize,
-                       const int64_t *ep, const int32_t *ex, int k, int32_t *ti, float *tv, cudaStream_t st) {
+                       const int64_t *ep, const int32_t *ex, int k, int32_t *ti, float *tv, void *workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
     const size_t smem = sizeof(tc::Smem) + 1024;
-    LGCN_CUDA(cudaFuncSetAttribute(tc::score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = cdiv(uend - ub, tc::BM);
-    tc::score_topk_tc_kernel<<<grid, tc::THREADS, smem, st>>>(ue, ie, I, ub, uend, normalize, ep, ex, k, ti, tv);
+    const int64_t tiles = (I + tc::BN - 1) / tc::BN;
+    if (workspace) {
+        LGCN_REQUIRE(workspace_bytes >= (size_t)tiles * 2 * tc::B_BYTES && ((uintptr_t)workspace & 127) == 0, LGCN_E_WORKSPACE,
+                     "score_topk: workspace %zu < %zu bytes (or not 128-byte aligned)", workspace_bytes,
+                     (size_t)tiles * 2 * tc::B_BYTES);
+        tc::pack_items_kernel<<<(unsigned)tiles, 256, 0, st>>>(ie, I, normalize, (unsigned char *)workspace);
+        LGCN_LAUNCH_CHECK();
+        LGCN_CUDA(cudaFuncSetAttribute(tc::score_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::score_topk_tc_kernel<true><<<grid, tc::THREADS_PACKED, smem, st>>>(ue, ie, (const unsigned char *)workspace, I, ub, uend,
+                                                                                normalize, ep, ex, k, ti, tv);
+    } else {
+        LGCN_CUDA(cudaFuncSetAttribute(tc::score_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::score_topk_tc_kernel<false><<<grid, tc::THREADS, smem, st>>>(ue, ie, nullptr, I, ub, uend, normalize, ep, ex, k, ti, tv);
+    }
     LGCN_LAUNCH_CHECK();
     return LGCN_OK;
+}
+
+size_t score_topk_tc_workspace_bytes(int64_t I) {
+    return (size_t)((I + tc::BN - 1) / tc::BN) * 2 * tc::B_BYTES;
 }
 
 }  // namespace lgcn

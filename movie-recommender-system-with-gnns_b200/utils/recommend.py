@@ -16,7 +16,8 @@ SCORE_AUTO, SCORE_FFMA, SCORE_TENSOR = 0, 1, 2
 
 def score_topk(user_rows: torch.Tensor, item_rows: torch.Tensor, k: int, normalize: bool = True,
                excl_ptr: Optional[torch.Tensor] = None, excl_idx: Optional[torch.Tensor] = None,
-               u_begin: int = 0, u_end: Optional[int] = None, algo: int = SCORE_AUTO) -> Tuple[torch.Tensor, torch.Tensor]:
+               u_begin: int = 0, u_end: Optional[int] = None, algo: int = SCORE_AUTO,
+               pack_items: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """top-k items per user by (score desc, id asc), score = <u, i> of (optionally L2-normalised)
     rows, items in the user's exclusion row removed.  ``excl_ptr`` [U+1] int64 / ``excl_idx`` int32
     sorted per row (CSR of train user->movie edges).  Returns (idx [n,k] int32, val [n,k])."""
@@ -34,9 +35,13 @@ def score_topk(user_rows: torch.Tensor, item_rows: torch.Tensor, k: int, normali
     if excl_ptr is not None:
         ep = require_cuda(excl_ptr, "excl_ptr", torch.int64).contiguous()
         ex = require_cuda(excl_idx, "excl_idx", torch.int32).contiguous()
+    ws = None
+    if algo != SCORE_FFMA and k <= 32 and pack_items:       # tensor-core kernel: pre-packed item tiles fetched by TMA
+        ws = torch.empty(lib().lgcn_score_topk_workspace_bytes(ir.size(0)), dtype=torch.uint8, device=dev)
     check(lib().lgcn_score_topk_ex(ur.data_ptr(), ir.data_ptr(), ir.size(0), u_begin, u_end, int(normalize),
                                    None if ep is None else ep.data_ptr(), None if ex is None else ex.data_ptr(),
-                                   k, idx.data_ptr(), val.data_ptr(), algo, stream_ptr(dev)))
+                                   k, idx.data_ptr(), val.data_ptr(), algo, None if ws is None else ws.data_ptr(),
+                                   0 if ws is None else ws.numel(), stream_ptr(dev)))
     return idx, val
 
 

@@ -100,17 +100,21 @@ def _check_topk(ids, vals, oids, ovals, tol):
     return float(safe.float().mean())
 
 
-@pytest.mark.parametrize("algo", [rec.SCORE_FFMA, rec.SCORE_TENSOR], ids=["ffma", "tcgen05"])
+ALGOS = [(rec.SCORE_FFMA, False), (rec.SCORE_TENSOR, True), (rec.SCORE_TENSOR, False)]
+ALGO_IDS = ["ffma", "tcgen05-tma-packed", "tcgen05-producer-warps"]
+
+
+@pytest.mark.parametrize("algo,pack", ALGOS, ids=ALGO_IDS)
 @pytest.mark.parametrize("shape,k,normalize", [("tiny", 20, True), ("ml100k", 20, True), ("ml100k", 10, False),
                                                ("ml100k", 100, True), ("ml100k", 50, True), ("ml1m", 20, True)])
-def test_score_topk_vs_bruteforce_oracle(shape, k, normalize, algo):
+def test_score_topk_vs_bruteforce_oracle(shape, k, normalize, algo, pack):
     if algo == rec.SCORE_TENSOR and k > 32:
         pytest.skip("tensor-core kernel keeps k <= 32")
     g = synthetic.make_graph(shape, seed=0)
     u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 5)
     train = g.edges("train")
     ptr, idx = rec.exclusion_csr(train.to(DEV), g.num_users)
-    ids, vals = rec.score_topk(u0.to(DEV), i0.to(DEV), k, normalize, ptr, idx, algo=algo)
+    ids, vals = rec.score_topk(u0.to(DEV), i0.to(DEV), k, normalize, ptr, idx, algo=algo, pack_items=pack)
     um = train[:, train[0] < g.num_users]
     order = torch.sort(um[0], stable=True)[1]
     cnt = torch.bincount(um[0], minlength=g.num_users)
@@ -128,12 +132,12 @@ def test_score_topk_vs_bruteforce_oracle(shape, k, normalize, algo):
     assert (vals[:, :-1] >= vals[:, 1:]).all()
 
 
-@pytest.mark.parametrize("algo", [rec.SCORE_FFMA, rec.SCORE_TENSOR], ids=["ffma", "tcgen05"])
-def test_score_topk_user_range_no_exclusion_and_short_lists(algo):
+@pytest.mark.parametrize("algo,pack", ALGOS, ids=ALGO_IDS)
+def test_score_topk_user_range_no_exclusion_and_short_lists(algo, pack):
     gen = torch.Generator().manual_seed(3)
     u = torch.randn(300, 64, generator=gen)
     it = torch.randn(37, 64, generator=gen)                     # fewer items than one tile
-    ids, vals = rec.score_topk(u.to(DEV), it.to(DEV), 20, False, u_begin=130, u_end=263, algo=algo)
+    ids, vals = rec.score_topk(u.to(DEV), it.to(DEV), 20, False, u_begin=130, u_end=263, algo=algo, pack_items=pack)
     s = u[130:263].double() @ it.double().t()
     ov, oi = torch.topk(s, 20, dim=1)
     assert ids.shape == (133, 20)
@@ -142,7 +146,7 @@ def test_score_topk_user_range_no_exclusion_and_short_lists(algo):
     ptr = torch.zeros(301, dtype=torch.int64)
     ptr[1:] = 30
     ex = torch.arange(30, dtype=torch.int32)
-    ids, vals = rec.score_topk(u.to(DEV), it.to(DEV), 20, False, ptr.to(DEV), ex.to(DEV), 0, 1, algo=algo)
+    ids, vals = rec.score_topk(u.to(DEV), it.to(DEV), 20, False, ptr.to(DEV), ex.to(DEV), 0, 1, algo=algo, pack_items=pack)
     assert (ids[0, :7] >= 30).all() and (ids[0, 7:] == -1).all() and torch.isinf(vals[0, 7:]).all()
 
 
