@@ -251,15 +251,32 @@ def run_c2(args):
                 "achieved": b_layer / (layer_ms * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "traffic": ncu_traffic("rowtask_fwd_layer"), "algorithmic_bytes_per_launch": b_layer,
                 "avg_launch_ms": layer_ms,
-                "note": "table (56.7 MB) is L2-resident, so the kernel is bound by L2 gather latency/throughput "
-                        "(gather-model GB/s in spmm_full_graph), not by the compulsory HBM bytes"}
+                "note": "table (56.7 MB) is L2-resident, so the kernel is bound by the L2 gather rate, not by the compulsory "
+                        "HBM bytes: see l2_gather (gather-model bytes E*264 + N*256 per layer against the measured "
+                        "random-row-gather ceiling of the L2)"}
     roofline["frac"] = roofline["achieved"] / peak
+    roofline["l2_gather"] = {"achieved": spmm["gather_model_gbs"], "peak": spmm["l2_gather_ceiling_gbs"], "unit": "GB/s",
+                             "frac": spmm["frac_of_l2_gather_ceiling"], "peak_source": spmm["l2_gather_ceiling_how"]}
     roofline_adam = {"kernel": "clip_adam_kernel (dense step)", "bound": "hbm",
                      "achieved": adam_bytes / (adam_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "traffic": ncu_traffic("clip_adam"), "algorithmic_bytes_per_launch": adam_bytes,
                      "avg_launch_ms": adam_ms}
     roofline_adam["frac"] = roofline_adam["achieved"] / peak
-    n_sparse = sum(1 for gr in graphs_of(model, live) if tt.sparse_step_pays(gr))
+    # the kernel the epoch actually spends its time in: one persistent launch per epoch (epoch_kernel.cu).
+    # Algorithmic bytes per step: Adam state of the touched rows (p, m, v read + written) + the activation rows
+    # of the active nodes (y0..y_{K-1}, final, G, z tables, grad: written once, read once or K times) + indices.
+    grs = graphs_of(model, live)
+    step_bytes = 0
+    for gr in grs:
+        touched = gr.num_active + min(gr.num_triplets, g.num_items)
+        step_bytes += touched * 256 * 6 + gr.num_active * 256 * (2 * (2 * k + 3)) + gr.num_edges * 4 * (2 * k + 4)
+    roofline_step = {"kernel": "epoch_kernel (lgcn_train_steps_sparse: all sparse steps of an epoch in one launch)",
+                     "bound": "hbm", "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "algorithmic_bytes_per_launch": step_bytes, "avg_launch_ms": ms_per_step,
+                     "note": "latency-bound by construction: ~2 k rows and ~7 k edges per step, 2K+4 device-wide barriers "
+                             "per step; duration here is the whole epoch (kernel + end-of-epoch flush)"}
+    roofline_step["frac"] = roofline_step["achieved"] / peak
+    n_sparse = sum(1 for gr in grs if tt.sparse_step_pays(gr))
     # per epoch: the sparse batches run inside ONE persistent cooperative launch (epoch_kernel) followed by one
     # adam_replay_kernel (flush); a dense batch is launches_per_step(k, False) kernels
     launches = args.steps * ((2 if n_sparse else 0) + (len(live) - n_sparse) * launches_per_step(k, False))
@@ -277,7 +294,8 @@ def run_c2(args):
                       "step_kinds": f"{n_sparse} touched-rows (sparse) steps inside one persistent cooperative launch "
                                     f"(lgcn_train_steps_sparse) + {len(live) - n_sparse} dense steps per epoch"},
            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-           "roofline": roofline, "roofline_adam": roofline_adam, "dense_stage_ms_per_epoch": stage_ms,
+           "roofline": roofline, "roofline_adam": roofline_adam, "roofline_step_kernel": roofline_step,
+           "dense_stage_ms_per_epoch": stage_ms,
            "spmm_full_graph": spmm,
            "setup_ms": {"cluster_extract": extract_ms, "graph_build_100_batches": build_ms},
            "final_epoch_loss": losses[-1]}
@@ -369,9 +387,30 @@ def full_graph_propagation(model, train_dev, k, dev, peak):
     b_layer = 2 * n * 256 + 8 * e + 4 * (n + 1)                    # SURVEY.md sec.8(d) contract figure
     gather = e * 264 + n * 256 + 4 * (n + 1)
     model._graphs.clear()
+    # measured ceiling of this access shape: independent random 256-byte row gathers over a table of the same
+    # size, no index array, no dependent address (csrc/probe.cu) -- what the L2 can deliver at best
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    table = torch.randn(n, 64, device=dev)
+    sink = torch.zeros(sms * 6 * 16, device=dev)
+    rows_hw = 4096
+
+    def probe():
+        _lib.check(L.lgcn_probe_gather(table.data_ptr(), n, sms * 6, rows_hw, sink.data_ptr(), _lib.stream_ptr(dev)))
+    for _ in range(3):
+        probe()
+    pt = []
+    for _ in range(5):
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); probe(); z.record()
+        torch.cuda.synchronize()
+        pt.append(a.elapsed_time(z))
+    l2_peak = sms * 6 * 16 * rows_hw * 256 / (float(np.median(pt)) * 1e-3) / 1e9
+    gather_gbs = k * gather / (ms * 1e-3) / 1e9
     return {"edges": e, "layers": k, "ms": ms, "edges_per_s": e * k / (ms * 1e-3),
             "algorithmic_gbs": k * b_layer / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": k * b_layer / (ms * 1e-3) / 1e9 / peak,
-            "gather_model_gbs": k * gather / (ms * 1e-3) / 1e9}
+            "gather_model_gbs": gather_gbs, "l2_gather_ceiling_gbs": l2_peak, "frac_of_l2_gather_ceiling": gather_gbs / l2_peak,
+            "l2_gather_ceiling_how": "lgcn_probe_gather: random 256 B row gathers over an equally sized (L2-resident) table, "
+                                     "measured live"}
 
 
 # --------------------------------------------------------------------------------------------

@@ -469,3 +469,41 @@ def test_train_epoch_uses_sparse_steps_and_flushes():
 def _negs(train, nu, ni, seed):          # noqa: F811  (redefinition keeps the helper next to its users)
     gen = torch.Generator().manual_seed(seed)
     return torch.randint(0, ni, (int((train[0] < nu).sum()),), generator=gen)
+
+
+def test_full_size_ml25m_layer_vs_torch_scatter_and_adjoint():
+    """BASELINE config C2/C3 at FULL size (162,541 x 59,047, 22.5 M train edges): one LGConv layer against the
+    reference's own op sequence (PyG gcn_norm + index_select / mul / scatter_add) executed by
+    plain PyTorch on the same device, the adjoint identity <A x, y> = <x, A^T y>, and bit-exact degrees."""
+    g = synthetic.make_graph("ml25m", seed=0)
+    train = g.edges("train").to(DEV)
+    n = g.num_nodes
+    G = _lib.Graph(train, g.num_users, g.num_items)
+    row, col = train[0], train[1]
+    deg = torch.bincount(col, minlength=n)
+    assert torch.equal(G.in_degree(), deg) and torch.equal(G.out_degree(), torch.bincount(row, minlength=n))
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(n, 64, device=DEV, generator=gen)
+    y = torch.randn(n, 64, device=DEV, generator=gen)
+    conv = LGConv(g.num_users)
+    ax = conv(x, train)
+    dis = deg.to(torch.float32).pow(-0.5)
+    dis[torch.isinf(dis)] = 0
+    w = dis[row] * dis[col]
+    want = torch.zeros(n, 64, device=DEV).index_add_(0, col, w[:, None] * x.index_select(0, row))
+    assert normwise(ax, want) < 1e-5
+    # adjoint through autograd of the same operator (lgcn_spmm transpose = 1)
+    xg = x.clone().requires_grad_(True)
+    (conv(xg, train) * y).sum().backward()
+    aty = xg.grad
+    lhs = (ax.double() * y.double()).sum()
+    rhs = (x.double() * aty.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-5 * abs(float(lhs))
+    # K-layer fused forward = sum of powers / (K+1)^2 built from the single layer
+    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
+    m = _model(g.num_users, g.num_items, 3, u0, i0)
+    uf, itf = m(train)
+    e0 = torch.cat([u0, i0]).to(DEV)
+    e1 = conv(e0, train); e2 = conv(e1, train); e3 = conv(e2, train)
+    want_final = (e0 + e1 + e2 + e3) / 16.0
+    assert normwise(torch.cat([uf, itf]), want_final) < 1e-5
