@@ -76,9 +76,19 @@ adam_replay_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__
     const bool any_live = (__ballot_sync(FULL, live) & half_mask) != 0u;      // no lane has exited yet
     if (valid && any_live) {
         const float4 zero = f4zero();
-        for (int t = from + 1; t <= target; ++t) {
-            const AdamScalars a = adam_scalars(h, t);
-            adam_vec(p4, m4, v4, zero, 1.0f, a);
+        if (h.bc_table && target < h.bc_len) {
+            // steps chain only through one fma each for p, m, v: unrolling lets the sqrt / division sequences of
+            // neighbouring steps overlap (the flush is MUFU- and latency-bound, not bandwidth-bound)
+#pragma unroll 4
+            for (int t = from + 1; t <= target; ++t) {
+                const AdamScalars a = adam_scalars_tab(h, t);
+                adam_vec(p4, m4, v4, zero, 1.0f, a);
+            }
+        } else {
+            for (int t = from + 1; t <= target; ++t) {
+                const AdamScalars a = adam_scalars(h, t);
+                adam_vec(p4, m4, v4, zero, 1.0f, a);
+            }
         }
         *pp = p4; m[o] = m4; v[o] = v4;
     }
