@@ -144,6 +144,11 @@ int lgcn_graph_build_batched(const int64_t *edges, const int64_t *edge_off, int6
                              int64_t num_nodes, int64_t num_users, lgcn_graph *graphs, void *arena,
                              size_t arena_bytes, void *workspace, size_t workspace_bytes, void *stream);
 
+/* `batch.to(device)` (utils/train_test.py:87) for all lists of an epoch: HOST list b (contiguous [2,E_b] int64,
+ * pinned or pageable) -> dst + 2*edge_off[b] (device), one asynchronous copy per list on `stream`. */
+int lgcn_upload_lists(const int64_t *const *host_lists, const int64_t *edge_off, int64_t num_lists,
+                      int64_t *dst, void *stream);
+
 /* ---- K1/K2: propagation ----------------------------------------------------------------- */
 
 /* final[N,64] = (sum_{k=0..K} A^k e0) / (K+1)^2 with A[c,r] = dis[r] dis[c] per edge r->c

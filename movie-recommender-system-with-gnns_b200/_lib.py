@@ -30,7 +30,7 @@ EXPORTS = [
     "lgcn_bpr_fwd_bwd_range", "lgcn_clip_adam_rows", "lgcn_train_step_sparse", "lgcn_adam_flush",
     "lgcn_peer_barrier", "lgcn_score_topk_ex", "lgcn_graph_batched_sizes", "lgcn_graph_build_batched",
     "lgcn_train_steps_workspace_bytes", "lgcn_train_steps_sparse", "lgcn_probe_gather",
-    "lgcn_score_topk_workspace_bytes",
+    "lgcn_score_topk_workspace_bytes", "lgcn_upload_lists",
 ]
 
 
@@ -141,6 +141,7 @@ def lib():
     L.lgcn_graph_batched_sizes.argtypes = [c_int64, c_int64, c_void_p, POINTER(CBatchedSizes)]
     L.lgcn_graph_build_batched.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t,
                                            c_void_p, c_size_t, c_void_p]
+    L.lgcn_upload_lists.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     L.lgcn_probe_gather.argtypes = [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]
     L.lgcn_train_steps_workspace_bytes.argtypes = [c_int64]
     L.lgcn_train_steps_workspace_bytes.restype = c_size_t

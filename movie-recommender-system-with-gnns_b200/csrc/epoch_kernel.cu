@@ -24,8 +24,9 @@
 //     A  y0 = dis (.) e0 for the active rows                                                    |
 //     B  forward layers 1..K (barrier after each; the last forms the layer mean and 1/||.||)    |
 //     E  BPR over user rows (loss, user-row gradient, negative-item gradient by vector atomics) |
-//     F  BPR over item rows (positive-item gradient, owner computes); both write dis (.) G too  |
-//     G  backward layers 1..K (barrier after each); the last also forms the inactive negatives' grad |
+//     F  BPR over item rows (positive-item gradient, owner computes); both write dis (.) G too;
+//        + the gradient rows of the inactive negatives                                          |
+//     G  backward layers 1..K (barrier after each)                                              |
 //     J  clip + Adam step on the touched rows, restore the all-zero invariants, loss, prefetch
 //   Everybody meets at the end of the step.  Step 0 is prepared by all CTAs before the loop.
 // Stamp / list arrays are double-buffered by step parity so that preparing b+1 never disturbs b.
@@ -561,10 +562,38 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                           reinterpret_cast<float4 *>(Z1)[(size_t)row * D4 + l16] = f4scale(dis_of(din), cur);
                       }
                   });
+        // the INACTIVE negatives' gradient rows (nothing propagates to a row without edges): grad = G/(K+1)^2 + reg.
+        // Their dL/dfinal rows and the histogram are complete since the barrier after E; this phase has only the
+        // item rows' tasks, so the list fills otherwise idle warps.
+        {
+            float n0 = 0.f, n1 = 0.f;
+            const int cnt = __ldcg(cnt_cur);
+            for (int base = gw * 2; base < cnt; base += nw * 2) {
+                const int idx = base + half;
+                float4 g = f4zero();
+                float reg = 0.f;
+                if (idx < cnt) {
+                    const int item = __ldcg(list_cur + idx), row = U + item;
+                    g = f4scale(c0, ldcg4(G4 + (size_t)row * D4 + l16));
+                    G4[(size_t)row * D4 + l16] = f4zero();
+                    const int c = __ldcg(a.neg_count + item);
+                    if (c) {
+                        const float4 e = ldcg4(w.row4(row) + l16);
+                        f4fma(g, reg_coef * (float)c, e);
+                        reg = (float)c * f4dot(e, e);
+                    }
+                    reinterpret_cast<float4 *>(a.grad)[(size_t)row * D4 + l16] = g;
+                }
+                n1 += warp_sum(f4dot(g, g));
+                n0 += warp_sum(reg);
+            }
+            if (lane == 0 && n0 != 0.f) atomicAdd(acc_cur + 1, (double)n0);
+            if (lane == 0 && n1 != 0.f) atomicAdd(acc_cur + 2, (double)n1);
+        }
         grid_barrier(bar_main, tgt_main, nmain);
         stamp(a.prof, b, ps, gtid);
 
-        // ---- G: backward layers 1..K (Horner); the last one also serves the inactive negatives ----
+        // ---- G: backward layers 1..K (Horner) ------------------------------------------------------
         ex0 = 0.f;
         for (int j = 1; j <= K; ++j) {
             const float *src = (j & 1) ? Z1 : Z0;
@@ -589,26 +618,6 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                           }
                       });
             if (last) {
-                const int cnt = __ldcg(cnt_cur);
-                for (int base = gw * 2; base < cnt; base += nw * 2) {
-                    const int idx = base + half;
-                    float4 g = f4zero();
-                    float reg = 0.f;
-                    if (idx < cnt) {
-                        const int item = __ldcg(list_cur + idx), row = U + item;
-                        g = f4scale(c0, ldcg4(G4 + (size_t)row * D4 + l16));
-                        G4[(size_t)row * D4 + l16] = f4zero();
-                        const int c = __ldcg(a.neg_count + item);
-                        if (c) {
-                            const float4 e = ldcg4(w.row4(row) + l16);
-                            f4fma(g, reg_coef * (float)c, e);
-                            reg = (float)c * f4dot(e, e);
-                        }
-                        reinterpret_cast<float4 *>(a.grad)[(size_t)row * D4 + l16] = g;
-                    }
-                    ex1 += warp_sum(f4dot(g, g));
-                    ex0 += warp_sum(reg);
-                }
                 if (lane == 0 && ex0 != 0.f) atomicAdd(acc_cur + 1, (double)ex0);
                 if (lane == 0 && ex1 != 0.f) atomicAdd(acc_cur + 2, (double)ex1);
             }

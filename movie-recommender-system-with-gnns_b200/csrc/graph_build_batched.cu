@@ -418,3 +418,20 @@ extern "C" int lgcn_graph_build_batched(const int64_t *edges, const int64_t *edg
     }
     return LGCN_OK;
 }
+
+// `batch.to(device)` for all lists of an epoch in one call: list b (its contiguous [2,E_b] int64 tensor in HOST
+// memory, pinned or pageable) goes to dst + 2 * edge_off[b] -- the layout lgcn_graph_build_batched reads.  One
+// cudaMemcpyAsync per list (asynchronous for pinned sources, staged by the driver for pageable ones).
+extern "C" int lgcn_upload_lists(const int64_t *const *host_lists, const int64_t *edge_off, int64_t B, int64_t *dst,
+                                 void *stream) {
+    using namespace lgcn;
+    LGCN_REQUIRE(host_lists && edge_off && dst && B >= 1, LGCN_E_INVALID, "upload_lists: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t b = 0; b < B; ++b) {
+        const int64_t e = edge_off[b + 1] - edge_off[b];
+        LGCN_REQUIRE(e >= 0 && (e == 0 || host_lists[b]), LGCN_E_INVALID, "upload_lists: bad list %lld", (long long)b);
+        if (e == 0) continue;
+        LGCN_CUDA(cudaMemcpyAsync(dst + 2 * edge_off[b], host_lists[b], sizeof(int64_t) * 2 * (size_t)e, cudaMemcpyHostToDevice, st));
+    }
+    return LGCN_OK;
+}

@@ -11,6 +11,7 @@ Two ways through ``train``:
 """
 from __future__ import annotations
 
+import ctypes
 from ctypes import byref
 from typing import Optional, Sequence, Tuple
 
@@ -178,7 +179,7 @@ class _Stage:
     """Buffers the host-batch pipeline reuses from epoch to epoch (no per-epoch cudaMalloc)."""
 
     def __init__(self):
-        self.edges = self.arena = self.workspace = self.pinned = self.current = None
+        self.edges = self.arena = self.workspace = self.current = self.uploading = None
 
 
 def train_step(model, optimizer: FusedAdam, edge_index: torch.Tensor, neg: Optional[torch.Tensor] = None,
@@ -237,6 +238,7 @@ class _SparseRun:
         self.model, self.opt, self.device = model, optimizer, device
         self.weights, self.slots, self.cap = weights, slots, cap
         self.graphs, self.edges = [], []
+        self.cg = None                    # optional: a ready-made contiguous CGraph array covering exactly the run
 
     def add(self, g, num_edges: int):
         self.graphs.append(g)
@@ -249,13 +251,14 @@ class _SparseRun:
         slot0 = len(self.weights)
         if slot0 + b > self.cap:
             raise LgcnError(f"more than {self.cap} batches in one epoch: enlarge FusedAdam.losses")
-        _launch_steps(self.model, self.opt, self.graphs, None, self.opt.losses.data_ptr() + 4 * slot0, 5e-3, self.device)
+        _launch_steps(self.model, self.opt, self.graphs, None, self.opt.losses.data_ptr() + 4 * slot0, 5e-3, self.device,
+                      self.cg if self.cg is not None and len(self.cg) == b else None)
         self.weights.extend(self.edges)
         self.slots.extend(range(slot0, slot0 + b))
         self.graphs, self.edges = [], []
 
 
-def _launch_steps(model, opt, graphs, neg_all, loss_ptr, bpr_coeff, device) -> None:
+def _launch_steps(model, opt, graphs, neg_all, loss_ptr, bpr_coeff, device, cg=None) -> None:
     """One lgcn_train_steps_sparse call for ``graphs`` (all with triplets); ``neg_all``: the steps'
     negatives back to back, sampled here when None."""
     b = len(graphs)
@@ -279,7 +282,8 @@ def _launch_steps(model, opt, graphs, neg_all, loss_ptr, bpr_coeff, device) -> N
         opt.dirty = False
     opt.pending = True
     opt._count_step(b)
-    cg = (CGraph * b)(*[g.c for g in graphs])
+    if cg is None:
+        cg = (CGraph * b)(*[g.c for g in graphs])
     uw, iw = model.user_embedding.weight, model.item_embedding.weight
     if not (uw.is_contiguous() and iw.is_contiguous()):
         raise LgcnError("embedding weights must be contiguous")
@@ -308,8 +312,8 @@ def train_steps(model, optimizer: FusedAdam, edge_indices: Sequence[torch.Tensor
 
 def _run_staged(model, optimizer: "FusedAdam", eis, device, weights, slots, cap) -> None:
     """The loop body of utils/train_test.py:86-101 for a run of HOST-resident batches:
-    ``batch.to(device)`` becomes one upload of all the edge lists (straight from pinned tensors, or packed
-    through a pinned staging buffer), the per-batch normalisation / CSR becomes ONE batched build (K0b),
+    ``batch.to(device)`` becomes one upload call for all the edge lists (``lgcn_upload_lists``), the per-batch
+    normalisation / CSR becomes ONE batched build (K0b),
     the negatives of a run of steps come from one ``randint`` (utils/helpers.py:79-80: uniform, no
     rejection; neg k pairs with the k-th user->movie edge), then the steps run in loader order -- sparse
     ones inside one persistent launch, dense ones one call each."""
@@ -320,26 +324,27 @@ def _run_staged(model, optimizer: "FusedAdam", eis, device, weights, slots, cap)
     tot = int(off[-1])
     if st.edges is None or st.edges.numel() < 2 * tot or st.edges.device != device:
         st.edges = torch.empty(int(2.5 * tot) + 64, dtype=torch.int64, device=device)
-    flat = [ei.contiguous().reshape(-1) for ei in eis]
-    if all(f.is_pinned() for f in flat):
-        for f, o in zip(flat, off[:-1]):
-            st.edges[2 * int(o): 2 * int(o) + f.numel()].copy_(f, non_blocking=True)
-    else:
-        if st.pinned is None or st.pinned.numel() < 2 * tot:
-            st.pinned = torch.empty(int(2.5 * tot) + 64, dtype=torch.int64, pin_memory=True)
-        torch.cat(flat, out=st.pinned[: 2 * tot])
-        st.edges[: 2 * tot].copy_(st.pinned[: 2 * tot], non_blocking=True)
+    # one C call issues the B copies (asynchronous from pinned tensors, driver-staged from pageable ones)
+    keep = [ei if ei.is_contiguous() else ei.contiguous() for ei in eis]
+    ptrs = (ctypes.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
+    check(lib().lgcn_upload_lists(ptrs, off.ctypes.data, len(keep), st.edges.data_ptr(), stream_ptr(device)))
+    st.uploading = keep                  # the host tensors must outlive the asynchronous copies
     bg = BatchedGraphs(st.edges, off, model.num_users, model.num_items, st.arena, st.workspace)
     st.arena, st.workspace, st.current = bg.arena, bg.workspace, bg
     run = _SparseRun(model, optimizer, device, weights, slots, cap)
+    whole = True                          # every list joins one run: the build's own struct array serves as is
     for g, e in zip(bg.graphs, sizes):
         if g.num_triplets == 0:
+            whole = False
             continue                      # the reference would produce NaN here (App. B #13)
         if EPOCH_KERNEL and sparse_step_pays(g):
             run.add(g, e)
             continue
+        whole = False
         run.flush()
         _single_step(model, optimizer, g, e, device, weights, slots, cap)
+    if whole:
+        run.cg = bg._cg
     run.flush()
 
 
@@ -464,7 +469,10 @@ def _train_epoch_fused(model, optimizer: "FusedAdam", train_loader, device) -> f
     if not weights:
         return float("nan")
     w = torch.tensor(weights, dtype=torch.float64)
-    losses = optimizer.losses[torch.tensor(slots, device=optimizer.losses.device)].double().cpu()   # the only sync
+    if slots == list(range(slots[0], slots[0] + len(slots))):
+        losses = optimizer.losses[slots[0]: slots[0] + len(slots)].cpu().double()                    # the only sync
+    else:
+        losses = optimizer.losses[torch.tensor(slots, device=optimizer.losses.device)].cpu().double()
     return float((losses * w).sum() / w.sum())
 
 

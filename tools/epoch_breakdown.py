@@ -98,8 +98,9 @@ st = opt.stage
 
 
 def upload():
-    for f, o in zip(eis, off[:-1]):
-        st.edges[2 * int(o): 2 * int(o) + f.numel()].copy_(f.reshape(-1), non_blocking=True)
+    import ctypes
+    ptrs = (ctypes.c_void_p * len(eis))(*[t.data_ptr() for t in eis])
+    _lib.check(_lib.lib().lgcn_upload_lists(ptrs, off.ctypes.data, len(eis), st.edges.data_ptr(), _lib.stream_ptr(dev)))
 
 
 print("upload 100 lists: device %.2f ms, host %.2f ms" % timed(upload))
