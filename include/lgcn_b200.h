@@ -89,6 +89,10 @@ typedef struct lgcn_graph {
     int32_t row_split;               /* max edges per task used for this graph                */
     const int32_t *active_list;      /* [num_active] ascending ids of the active nodes        */
     int32_t *sched;                  /* [2] zero between launches: dynamic task scheduler state */
+    int32_t in_src_sorted;           /* 1: inside every CSR-by-target row the source ids ascend (true for edge lists in
+                                        the reference's (row, col) order and their subsets) -- lets a rank find its own
+                                        users' slice of an item row by bisection (lgcn_bpr_fwd_bwd_range) */
+    int32_t reserved0;
 } lgcn_graph;
 
 /* ---- K0: graph build ------------------------------------------------------------------ */

@@ -53,7 +53,7 @@ class CGraph(Structure):
         ("n_in_slots", c_int32), ("n_out_slots", c_int32),
         ("partials", c_void_p), ("slot_counters", c_void_p),
         ("num_active", c_int32), ("row_split", c_int32), ("active_list", c_void_p),
-        ("sched", c_void_p),
+        ("sched", c_void_p), ("in_src_sorted", c_int32), ("reserved0", c_int32),
     ]
 
 

@@ -157,11 +157,33 @@ struct BprItemOp {
     float invP;
     float *G;
     int ub, ue;                 // only triplets of users in [ub,ue) are accumulated (sharded path)
+    int sorted;                 // the row's source ids ascend: the slice of users in [ub,ue) is found by bisection
+
+    // first position in [lo,hi) whose source id is >= key: 32-ary search, one probe per lane and round
+    __device__ __forceinline__ int lower_bound32(int lo, int hi, int key, int lane) const {
+        while (hi - lo > 32) {
+            const int step = (hi - lo + 31) / 32;                       // probes at lo + step*(lane+1) - 1
+            const int pos = min(lo + step * (lane + 1) - 1, hi - 1);
+            const unsigned less = __ballot_sync(FULL, __ldg(in_nbr + pos) < key);
+            const int k = __popc(less);                                  // probes 0..k-1 are < key (ascending row)
+            const int nlo = k == 0 ? lo : min(lo + step * k, hi);
+            const int nhi = k == 32 ? hi : min(lo + step * (k + 1) - 1, hi - 1) + 1;
+            lo = nlo; hi = nhi;
+        }
+        const int pos = lo + lane;
+        const unsigned less = __ballot_sync(FULL, pos < hi && __ldg(in_nbr + pos) < key);
+        return lo + __popc(less);
+    }
 
     __device__ __forceinline__ void accumulate(int, int begin, int end, int lane, float4 &acc, float &sc,
                                                float &, float &) const {
         const int l16 = lane & 15;
         const float4 *F4 = reinterpret_cast<const float4 *>(F);
+        if (sorted && end - begin > 8) {                                 // this rank's users form one contiguous slice
+            const int b2 = lower_bound32(begin, end, ub, lane);
+            end = lower_bound32(b2, end, ue, lane);
+            begin = b2;
+        }
         for_each_edge<TripItemB, UNROLL>(
             begin, end, lane,
             [&](int e) {
@@ -251,7 +273,8 @@ int bpr_impl(const lgcn_graph *g, const float *F, const float *rnorm, const int6
         BprUserOp<true> a{accum, nullptr, g->out_nbr, g->out_trip, neg, F, rnorm, g->num_users, invP, G,
                           neg_count, scratch, nullptr, Table{}, 0.f};
         LGCN_CUDA(launch_rowtasks(a, g->out_tasks, utb, ute, g->partials, g->slot_counters, g->sched, st));
-        BprItemOp b{nullptr, nullptr, g->in_nbr, g->in_trip, F, rnorm, scratch, invP, G, urb, ure};
+        BprItemOp b{nullptr, nullptr, g->in_nbr, g->in_trip, F, rnorm, scratch, invP, G, urb, ure,
+                    (g->in_src_sorted && (urb > 0 || ure < g->num_users)) ? 1 : 0};
         LGCN_CUDA(launch_rowtasks(b, g->in_tasks, g->n_in_user_tasks, g->n_in_tasks, g->partials,
                                   g->slot_counters, g->sched, st));
     } else {
@@ -272,7 +295,7 @@ int bpr_sparse_impl(const lgcn_graph *g, const float *F, const float *rnorm, con
     BprUserOp<true, true> a{accum, nullptr, g->out_nbr, g->out_trip, neg, F, rnorm, g->num_users, invP, G,
                             neg_count, scratch, g->active, Table{user_w, item_w, g->num_users}, c0};
     LGCN_CUDA(launch_rowtasks(a, g->out_tasks, 0, g->n_out_user_tasks, g->partials, g->slot_counters, g->sched, st));
-    BprItemOp b{nullptr, nullptr, g->in_nbr, g->in_trip, F, rnorm, scratch, invP, G, 0, g->num_users};
+    BprItemOp b{nullptr, nullptr, g->in_nbr, g->in_trip, F, rnorm, scratch, invP, G, 0, g->num_users, 0};
     LGCN_CUDA(launch_rowtasks(b, g->in_tasks, g->n_in_user_tasks, g->n_in_tasks, g->partials, g->slot_counters, g->sched, st));
     return LGCN_OK;
 }

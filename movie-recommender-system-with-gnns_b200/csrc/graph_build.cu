@@ -14,7 +14,7 @@
 namespace lgcn {
 
 enum { META_P = 0, META_BAD = 1, META_IN_TASKS, META_OUT_TASKS, META_IN_USER_TASKS, META_OUT_USER_TASKS,
-       META_IN_SLOTS, META_OUT_SLOTS, META_ACTIVE, META_COUNT = 16 };
+       META_IN_SLOTS, META_OUT_SLOTS, META_ACTIVE, META_UNSORTED, META_COUNT = 16 };
 
 struct IsUser {
     int num_users;
@@ -47,6 +47,13 @@ __global__ void fill_csr_kernel(const int *__restrict__ eid_sorted, const int *_
     const int e = eid_sorted[s];
     nbr[s] = other32[e];
     trip[s] = row32[e] < U ? trip_id[e] : -1;
+}
+
+// counts positions where two neighbouring entries of the same CSR row have descending neighbour ids
+__global__ void unsorted_kernel(const int *__restrict__ keys_sorted, const int *__restrict__ nbr, int64_t E, long long *meta) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s + 1 < E && keys_sorted[s] == keys_sorted[s + 1] && nbr[s] > nbr[s + 1])
+        atomicAdd((unsigned long long *)(meta + META_UNSORTED), 1ull);
 }
 
 // ptr[n] = first position whose sorted key is >= n (n = 0..N)
@@ -225,6 +232,8 @@ extern "C" int lgcn_graph_build(const int64_t *edge_index, int64_t E, int64_t N,
         LGCN_LAUNCH_CHECK();
         ptr_kernel<<<gN, T, 0, st>>>(w.keys_sorted, E, N, in_ptr);
         LGCN_LAUNCH_CHECK();
+        unsorted_kernel<<<gE, T, 0, st>>>(w.keys_sorted, (const int *)g->in_nbr, E, w.meta);
+        LGCN_LAUNCH_CHECK();
         // CSR by source
         tb = w.cub_bytes;
         LGCN_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.row32, w.keys_sorted, w.eid, w.eid_sorted,
@@ -272,5 +281,7 @@ extern "C" int lgcn_graph_build(const int64_t *edge_index, int64_t E, int64_t N,
     g->n_out_slots = (int32_t)meta[META_OUT_SLOTS];
     g->num_active = (int32_t)meta[META_ACTIVE];
     g->row_split = split;
+    g->in_src_sorted = meta[META_UNSORTED] == 0 ? 1 : 0;
+    g->reserved0 = 0;
     return LGCN_OK;
 }

@@ -415,6 +415,8 @@ extern "C" int lgcn_graph_build_batched(const int64_t *edges, const int64_t *edg
         g->row_split = (int32_t)(eb < LGCN_SMALL_GRAPH ? LGCN_ROW_SPLIT_SMALL : LGCN_ROW_SPLIT);
         g->active_list = a.active_list + m[M_ACTIVE_BASE];
         g->sched = a.sched;
+        g->in_src_sorted = 0;            // not needed by the single-GPU steps these graphs serve
+        g->reserved0 = 0;
     }
     return LGCN_OK;
 }
