@@ -60,6 +60,7 @@ constexpr int EP_THREADS = EP_WARPS * 32;
 struct StepDesc {
     const lgcn_task *in_tasks, *out_tasks;
     const int32_t *in_nbr, *in_trip, *out_nbr, *out_trip;
+    const float *dis;            // [N] in-degree^-1/2 of THIS batch graph (weight of a layer-1 in-edge)
     float *partials;
     int32_t *slot_counters;
     const int64_t *neg;
@@ -87,7 +88,8 @@ struct EpochArgs {
     double *accum;       // [2][4], by step parity
     int32_t *counts;     // [2] length of neg_list, by step parity
     unsigned *bar;       // monotonic arrival counters: [0] all CTAs, [32] main CTAs, [64] helper CTAs
-    int num_helpers;     // CTAs [gridDim.x - num_helpers, gridDim.x) prepare the next step
+    int num_helpers;     // how many CTAs prepare the next step (0: single-step run, everybody is MAIN)
+    int main_sms;        // SMs [0, main_sms) host the MAIN CTAs, the others the helpers
     float bpr_coeff;
     long long *prof;     // optional [num_steps][16] globaltimer stamps at the phase boundaries (diagnostics)
 };
@@ -103,11 +105,38 @@ __device__ __forceinline__ void stamp(long long *prof, int b, int &slot, int gti
     ++slot;
 }
 
+#ifdef EP_TRACE
+// Diagnostic build (tools/epoch_trace.py): every CTA records when it arrives at and when it leaves each barrier.
+__device__ long long *g_trace;            // [num_steps][16][gridDim.x][2]
+__device__ long long *g_trace_warp;       // [num_steps][16][gridDim.x][8]: when each WARP reached the barrier
+__device__ int *g_trace_smid;             // [gridDim.x]
+__device__ __forceinline__ long long gtimer() {
+    long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    return now;
+}
+#define EP_TRACE_AT(b, slot, which)                                                                     \
+    do {                                                                                                \
+        if (g_trace && threadIdx.x == 0 && (slot) < 16)                                                 \
+            g_trace[(((size_t)(b) * 16 + (slot)) * gridDim.x + blockIdx.x) * 2 + (which)] = gtimer();   \
+    } while (0)
+#define EP_TRACE_WARP(b, slot)                                                                           \
+    do {                                                                                                \
+        if (g_trace_warp && (threadIdx.x & 31) == 0 && (slot) < 16)                                     \
+            g_trace_warp[(((size_t)(b) * 16 + (slot)) * gridDim.x + blockIdx.x) * 8 + (threadIdx.x >> 5)] = gtimer(); \
+    } while (0)
+#else
+#define EP_TRACE_AT(b, slot, which) do { } while (0)
+#define EP_TRACE_WARP(b, slot) do { } while (0)
+#endif
+
 // Arrive (release) on a monotonic counter, wait (acquire) until `count` more CTAs have arrived than at
 // the previous barrier on it.  bar.sync before/after extends the ordering to the whole CTA.
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned count) {
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned count, int tb = 0, int tslot = 16) {
+    EP_TRACE_WARP(tb, tslot);
     __syncthreads();
     target += count;
+    EP_TRACE_AT(tb, tslot, 0);
     if (threadIdx.x == 0) {
         unsigned cur;
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(bar), "r"(1u) : "memory");
@@ -115,8 +144,60 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar) : "memory");
         } while ((int)(cur - target) < 0);
     }
+    EP_TRACE_AT(tb, tslot, 1);
     __syncthreads();
 }
+
+// The same barrier in two halves: work placed between arrive and wait overlaps the wait.  Only work that
+// reads launch-immutable data and writes CTA-private state may go there.
+__device__ __forceinline__ void barrier_arrive(unsigned *bar, int tb = 0, int tslot = 16) {
+    EP_TRACE_WARP(tb, tslot);
+    __syncthreads();
+    EP_TRACE_AT(tb, tslot, 0);
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(bar), "r"(1u) : "memory");
+}
+__device__ __forceinline__ void barrier_wait(unsigned *bar, unsigned &target, unsigned count, int tb = 0, int tslot = 16) {
+    target += count;
+    if (threadIdx.x == 0) {
+        unsigned cur;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar) : "memory");
+        } while ((int)(cur - target) < 0);
+    }
+    EP_TRACE_AT(tb, tslot, 1);
+    __syncthreads();
+}
+
+// Per-CTA sum of two per-warp scalars, then ONE double atomic per CTA and target: with one atomic per warp the
+// ~4 k same-address atomics of a phase serialised at the L2 and delayed every CTA's arrival at the barrier.
+// Contains a __syncthreads(); the caller's grid barrier orders the reuse of `red`.
+__device__ __forceinline__ void cta_add2(float (*red)[2], int lane, float v0, float v1, double *d0, double *d1) {
+    if (lane == 0) { red[threadIdx.x >> 5][0] = v0; red[threadIdx.x >> 5][1] = v1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < EP_THREADS / 32; ++i) { s0 += (double)red[i][0]; s1 += (double)red[i][1]; }
+        if (d0 && s0 != 0.0) atomicAdd(d0, s0);
+        if (d1 && s1 != 0.0) atomicAdd(d1, s1);
+    }
+}
+
+// Per-warp shared-memory image of the step's work.  Main warp gw owns tasks gw, gw + nw, ... of both task
+// lists in EVERY phase of a step, so the descriptors and index runs of its first EP_CT tasks per list are
+// fetched once per step (during the wait of the previous step's last barrier) instead of heading every
+// phase with a descriptor -> index -> row chain of dependent L2 round trips.  Everything cached is
+// immutable for the launch.  Tasks beyond EP_CT per warp, or longer than EP_CE edges, use the global path.
+constexpr int EP_CT = 2;
+constexpr int EP_CE = LGCN_ROW_SPLIT_SMALL;
+constexpr int DIR_IN = 0, DIR_OUT = 1;
+struct __align__(16) WarpCache {
+    int4 ta[2][EP_CT], tc[2][EP_CT];      // [direction][slot]: the lgcn_task
+    int32_t nbr[2][EP_CT][EP_CE];         // in: source ids; out: target ids
+    int32_t trip[2][EP_CT][EP_CE];        // in (item rows) / out (user rows): triplet number of the edge
+    int32_t ng[EP_CT][EP_CE];             // out, user rows: num_users + negative item of the triplet
+    float wgt[EP_CT][EP_CE];              // in: dis[source]  (layer 1 reads e0 itself, no pre-scaled table)
+};
 
 // for_each_edge (rowtask.cuh) with the 32-edge chunk loop left ROLLED: the persistent kernel holds every
 // phase's code at once, and sixteen inlined copies of each edge body made it 220 KB -- every phase then
@@ -155,10 +236,12 @@ struct Tab {                        // mutable e0 = (user_w, item_w)
 
 struct Nbr {
     int nbr;
+    float w;
     float4 v;
     __device__ __forceinline__ Nbr shfl(int src_lane) const {
         Nbr r;
         r.nbr = __shfl_sync(FULL, nbr, src_lane);
+        r.w = __shfl_sync(FULL, w, src_lane);
         r.v = f4zero();
         return r;
     }
@@ -166,29 +249,69 @@ struct Nbr {
 
 __device__ __forceinline__ float dis_of(int deg_in) { return deg_in > 0 ? 1.0f / sqrtf((float)deg_in) : 0.f; }
 
-// raw[c] = sum over the task's edges of x[nbr]   (x written earlier in this launch -> ld.cg)
-__device__ __noinline__ void gather_sum(const int32_t *__restrict__ nbr, const float *x, int begin, int end, int lane,
-                                           float4 &acc) {
+// raw[c] = sum over the task's edges of x[nbr]   (x written earlier in this launch -> ld.cg).
+// c_nbr != null: the task's index run sits in shared memory (WarpCache), else nbr + begin.. in global memory.
+__device__ __noinline__ void gather_sum(const int32_t *__restrict__ nbr, const int32_t *c_nbr, const float *x, int begin,
+                                           int end, int lane, float4 &acc) {
     const int l16 = lane & 15;
     const float4 *x4 = reinterpret_cast<const float4 *>(x);
     for_each_edge_rolled<Nbr, EP_GATHER_UNROLL>(
         begin, end, lane,
-        [&](int e) { Nbr it; it.nbr = e >= 0 ? __ldg(nbr + e) : -1; it.v = f4zero(); return it; },
+        [&](int e) {
+            Nbr it;
+            it.nbr = e >= 0 ? (c_nbr ? c_nbr[e - begin] : __ldg(nbr + e)) : -1;
+            it.w = 0.f;
+            it.v = f4zero();
+            return it;
+        },
         [&](int, Nbr &it) { if (it.nbr >= 0) it.v = ldcg4(x4 + (size_t)it.nbr * D4 + l16); },
         [&](int, Nbr &it) { f4add(acc, it.v); });
 }
 
-// Walk tasks [tb,te) round-robin over all warps of the grid; same split-row protocol as rowtask_kernel.
+// Layer 1: raw[c] = sum dis[r] * e0[r] straight from the weight tables (the arithmetic of rowtask_kernel<FwdOp>'s
+// first layer: the scale rides in the fma), so no pre-scaled copy of the active rows is written first.
+__device__ __noinline__ void gather_sum_e0(const int32_t *__restrict__ nbr, const float *__restrict__ dis,
+                                              const int32_t *c_nbr, const float *c_wgt, const Tab &w, int begin, int end,
+                                              int lane, float4 &acc) {
+    const int l16 = lane & 15;
+    for_each_edge_rolled<Nbr, EP_GATHER_UNROLL>(
+        begin, end, lane,
+        [&](int e) {
+            Nbr it;
+            it.nbr = -1; it.w = 0.f; it.v = f4zero();
+            if (e >= 0) {
+                if (c_nbr) { it.nbr = c_nbr[e - begin]; it.w = c_wgt[e - begin]; }
+                else { it.nbr = __ldg(nbr + e); it.w = __ldg(dis + it.nbr); }
+            }
+            return it;
+        },
+        [&](int, Nbr &it) { if (it.nbr >= 0) it.v = ldcg4(w.row4(it.nbr) + l16); },
+        [&](int, Nbr &it) { f4fma(acc, it.w, it.v); });
+}
+
+// Walk the tasks [tb,te) of one list that belong to this warp (t = gw, gw + nw, ...: the same ownership in
+// every phase, which is what makes the WarpCache valid); same split-row protocol as rowtask_kernel.
+// accumulate(row, begin, end, cs, acc, sc): cs = cache slot holding the task's index runs, or -1.
 template <class Acc, class Epi>
-__device__ __forceinline__ void run_tasks(const lgcn_task *__restrict__ tasks, int tb, int te, float *partials,
-                                          int *counters, int gw, int nw, int lane, Acc accumulate, Epi epilogue) {
-    for (int t = tb + gw; t < te; t += nw) {
-        const int4 ta = __ldg(reinterpret_cast<const int4 *>(tasks + t));
-        const int4 tc = __ldg(reinterpret_cast<const int4 *>(tasks + t) + 1);
+__device__ __forceinline__ void run_tasks(const WarpCache &wc, int dir, const lgcn_task *__restrict__ tasks, int tb, int te,
+                                          float *partials, int *counters, int gw, int nw, int lane, Acc accumulate,
+                                          Epi epilogue) {
+    int ci = 0;
+    for (int t = gw; t < te; t += nw, ++ci) {
+        if (t < tb) continue;
+        int4 ta, tc;
+        if (ci < EP_CT) {
+            ta = wc.ta[dir][ci];
+            tc = wc.tc[dir][ci];
+        } else {
+            ta = __ldg(reinterpret_cast<const int4 *>(tasks + t));
+            tc = __ldg(reinterpret_cast<const int4 *>(tasks + t) + 1);
+        }
         const int row = ta.x, begin = ta.y, end = ta.z, slot = ta.w, part = tc.x, nparts = tc.y;
+        const int cs = (ci < EP_CT && end - begin <= EP_CE) ? ci : -1;
         float4 acc = f4zero();
         float sc = 0.f;
-        accumulate(row, begin, end, acc, sc);
+        accumulate(row, begin, end, cs, acc, sc);
         f4add(acc, f4shfl_xor16(acc));
         sc = warp_sum(sc);
         bool run = slot < 0;
@@ -205,10 +328,19 @@ __device__ __forceinline__ void run_tasks(const lgcn_task *__restrict__ tasks, i
                 __threadfence();
                 acc = f4zero();
                 sc = 0.f;
-                for (int i = 0; i < nparts; ++i) {
-                    const float *q = partials + (size_t)(first + i) * PARTIAL_STRIDE;
-                    f4add(acc, __ldcg(reinterpret_cast<const float4 *>(q) + (lane & 15)));
-                    sc += __ldcg(q + D);
+                // four slots per round trip, summed in slot order (deterministic)
+                for (int i = 0; i < nparts; i += 4) {
+                    float4 q4[4];
+                    float qs[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float *q = partials + (size_t)(first + min(i + u, nparts - 1)) * PARTIAL_STRIDE;
+                        q4[u] = __ldcg(reinterpret_cast<const float4 *>(q) + (lane & 15));
+                        qs[u] = __ldcg(q + D);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i + u < nparts) { f4add(acc, q4[u]); sc += qs[u]; }
                 }
                 if (lane == 0) counters[first] = 0;
                 run = true;
@@ -218,35 +350,94 @@ __device__ __forceinline__ void run_tasks(const lgcn_task *__restrict__ tasks, i
     }
 }
 
+// Fill this warp's cache for the step described by d (launch-immutable data only; called between the arrive
+// and the wait of a barrier).  Loads are issued stage by stage for all slots so the dependent round trips
+// (descriptor -> indices -> dis / negative) overlap across slots.
+__device__ __forceinline__ void fill_cache(WarpCache &wc, const StepDesc &d, int gw, int nw, int lane, int U) {
+    int4 ta[2][EP_CT], tc[2][EP_CT];
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+        const lgcn_task *tasks = dir == DIR_IN ? d.in_tasks : d.out_tasks;
+        const int nt = dir == DIR_IN ? d.n_in_tasks : d.n_out_tasks;
+#pragma unroll
+        for (int ci = 0; ci < EP_CT; ++ci) {
+            const int t = gw + ci * nw;
+            ta[dir][ci] = make_int4(0, 0, 0, -1);
+            tc[dir][ci] = make_int4(0, 1, 0, 0);
+            if (t < nt) {
+                ta[dir][ci] = __ldg(reinterpret_cast<const int4 *>(tasks + t));
+                tc[dir][ci] = __ldg(reinterpret_cast<const int4 *>(tasks + t) + 1);
+            }
+        }
+    }
+    int nb[2][EP_CT][EP_CE / 32], tr[2][EP_CT][EP_CE / 32];
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+        const int32_t *nbr = dir == DIR_IN ? d.in_nbr : d.out_nbr;
+        const int32_t *trp = dir == DIR_IN ? d.in_trip : d.out_trip;
+#pragma unroll
+        for (int ci = 0; ci < EP_CT; ++ci) {
+            const int begin = ta[dir][ci].y, len = ta[dir][ci].z - begin;
+            // triplet numbers: BPR walks the item rows of the by-target list and the user rows of the by-source list
+            const bool want_trip = dir == DIR_IN ? ta[dir][ci].x >= U : ta[dir][ci].x < U;
+#pragma unroll
+            for (int h = 0; h < EP_CE / 32; ++h) {
+                const int e = lane + 32 * h;
+                const bool ok = len <= EP_CE && e < len;
+                nb[dir][ci][h] = ok ? __ldg(nbr + begin + e) : -1;
+                tr[dir][ci][h] = ok && want_trip ? __ldg(trp + begin + e) : -1;
+            }
+        }
+    }
+#pragma unroll
+    for (int ci = 0; ci < EP_CT; ++ci) {
+#pragma unroll
+        for (int h = 0; h < EP_CE / 32; ++h) {
+            const int e = lane + 32 * h;
+            const int src = nb[DIR_IN][ci][h], t_out = tr[DIR_OUT][ci][h];
+            wc.wgt[ci][e] = src >= 0 ? __ldg(d.dis + src) : 0.f;
+            wc.ng[ci][e] = t_out >= 0 ? U + (int)__ldg(d.neg + t_out) : 0;
+        }
+    }
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir)
+#pragma unroll
+        for (int ci = 0; ci < EP_CT; ++ci) {
+            if (lane == 0) { wc.ta[dir][ci] = ta[dir][ci]; wc.tc[dir][ci] = tc[dir][ci]; }
+#pragma unroll
+            for (int h = 0; h < EP_CE / 32; ++h) {
+                wc.nbr[dir][ci][lane + 32 * h] = nb[dir][ci][h];
+                wc.trip[dir][ci][lane + 32 * h] = tr[dir][ci][h];
+            }
+        }
+    __syncwarp();
+}
+
 // Bring `row` up to optimiser step `target` by replaying zero-gradient Adam steps (adam_replay_kernel's
-// arithmetic).  One half-warp per row; returns this lane's 4 weights (zero for invalid rows).
-__device__ __forceinline__ float4 replay_row(bool valid, int row, int lane, int target, const Tab &w, float4 *m, float4 *v,
-                                             int32_t *row_step, const AdamHyper &h) {
-    const int l16 = lane & 15;
-    const int from = valid ? __ldcg(row_step + row) : target;
-    const bool need = valid && from < target;
-    float4 *pp = w.row4(valid ? row : 0) + l16;
-    const size_t o = (size_t)(valid ? row : 0) * D4 + l16;
-    float4 p4 = f4zero(), m4 = f4zero(), v4 = f4zero();
-    if (valid) p4 = ldcg4(pp);
-    if (need) { m4 = ldcg4(m + o); v4 = ldcg4(v + o); }
-    const bool live = m4.x != 0.f || m4.y != 0.f || m4.z != 0.f || m4.w != 0.f ||
-                      v4.x != 0.f || v4.y != 0.f || v4.z != 0.f || v4.w != 0.f;
-    const unsigned half_mask = 0xffffu << (lane & 16);
-    const bool any_live = (__ballot_sync(FULL, live) & half_mask) != 0u;
-    if (need && any_live) {
+// arithmetic, element by element).  ONE WARP per row, two elements per lane: the chain of a row is bound by the
+// instructions one warp can issue (an IEEE sqrt and two divisions per element and step), so a row spread over
+// 32 lanes finishes in half the time of the half-warp / float4 layout.
+__device__ __forceinline__ void replay_row(int row, int lane, int target, const Tab &w, float4 *m, float4 *v,
+                                           int32_t *row_step, const AdamHyper &h) {
+    const int from = __ldcg(row_step + row);
+    if (from >= target) return;                                       // warp-uniform
+    float2 *pp = reinterpret_cast<float2 *>(w.row4(row)) + lane;
+    float2 *mp = reinterpret_cast<float2 *>(m + (size_t)row * D4) + lane;
+    float2 *vp = reinterpret_cast<float2 *>(v + (size_t)row * D4) + lane;
+    float2 p2 = __ldcg(pp), m2 = __ldcg(mp), v2 = __ldcg(vp);
+    const bool live = m2.x != 0.f || m2.y != 0.f || v2.x != 0.f || v2.y != 0.f;
+    if (__any_sync(FULL, live)) {                                     // all-zero moments: the row does not move
         // iterations only chain through one fma each for p, m, v: unrolling lets the sqrt / division
         // sequences of neighbouring steps overlap
-        const float4 zero = f4zero();
-#pragma unroll 2
+#pragma unroll 4
         for (int t = from + 1; t <= target; ++t) {
             const AdamScalars a = adam_scalars_tab(h, t);
-            adam_vec(p4, m4, v4, zero, 1.0f, a);
+            adam_elem(p2.x, m2.x, v2.x, 0.f, a);
+            adam_elem(p2.y, m2.y, v2.y, 0.f, a);
         }
-        *pp = p4; m[o] = m4; v[o] = v4;
+        *pp = p2; *mp = m2; *vp = v2;
     }
-    if (need && l16 == 0) row_step[row] = target;
-    return p4;
+    if (lane == 0) row_step[row] = target;
 }
 
 // Touched by the step with number `tp` (its stamps live in act_p / flag_p)?  Such a row is left alone by
@@ -260,27 +451,31 @@ __device__ __forceinline__ bool touched_by(int row, int num_users, int tp, const
 // Replay the pending zero-gradient steps of a row set up to step `target`, behind ONE copy of the
 // (unrolled) Adam loop.  RP_ACTIVE: the first-part in-tasks' rows, which are also stamped as active in
 // step target+1;  RP_LIST: rows num_users + list[i].  Rows touched by step `target` itself are skipped.
+// Rows differ widely in pending steps (1 .. steps per epoch), so after its first (static) item a warp pulls
+// further items from a device queue (`queue`, zero on entry; the pull is issued before the current row is
+// processed so its latency hides behind the replay).
 enum { RP_ACTIVE = 0, RP_LIST = 1 };
 
 __device__ __noinline__ void replay_rows(int mode, const lgcn_task *__restrict__ tasks, const int32_t *list, int count,
                                          int target, Tab w, float4 *m, float4 *v, int32_t *row_step, int32_t *act_next,
-                                         const int32_t *act_p, const int32_t *flag_p, AdamHyper h, int gw, int nw, int lane) {
-    const int l16 = lane & 15, half = lane >> 4;
-    for (int base = gw * 2; base < count; base += nw * 2) {
-        const int i = base + half;
-        bool valid = i < count;
-        int row = 0;
-        if (valid) {
-            if (mode == RP_LIST) {
-                row = w.num_users + __ldcg(list + i);
-            } else {
-                row = __ldg(&tasks[i].row);
-                valid = __ldg(&tasks[i].part) == 0;          // first part of a split row speaks for the row
-                if (valid && l16 == 0) act_next[row] = target + 1;
-            }
-            if (valid) valid = !touched_by(row, w.num_users, target, act_p, flag_p);
+                                         const int32_t *act_p, const int32_t *flag_p, AdamHyper h, int gw, int nw, int lane,
+                                         int32_t *queue) {
+    int i = gw;
+    while (i < count) {                                               // warp-uniform
+        int nxt = 0;
+        if (lane == 0) nxt = nw + atomicAdd(queue, 1);
+        int row;
+        bool valid = true;
+        if (mode == RP_LIST) {
+            row = w.num_users + __ldcg(list + i);
+        } else {
+            row = __ldg(&tasks[i].row);
+            valid = __ldg(&tasks[i].part) == 0;                      // first part of a split row speaks for the row
+            if (valid && lane == 0) act_next[row] = target + 1;
         }
-        replay_row(valid, row, lane, target, w, m, v, row_step, h);
+        if (valid) valid = !touched_by(row, w.num_users, target, act_p, flag_p);
+        if (valid) replay_row(row, lane, target, w, m, v, row_step, h);
+        i = __shfl_sync(FULL, nxt, 0);
     }
 }
 
@@ -340,25 +535,76 @@ struct TripB {
 };
 
 __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const EpochArgs a) {
+    __shared__ WarpCache s_cache[EP_WARPS];
+    __shared__ float s_red[EP_WARPS][2];
+    WarpCache &wc = s_cache[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
     const int gw_all = blockIdx.x * EP_WARPS + (threadIdx.x >> 5), nw_all = gridDim.x * EP_WARPS;
-    const unsigned nblocks = gridDim.x, nhelp = a.num_helpers, nmain = gridDim.x - a.num_helpers;
-    const bool helper = blockIdx.x >= nmain;
-    // main CTAs index their work among themselves; helpers among themselves
-    const int gw = helper ? gw_all - (int)nmain * EP_WARPS : gw_all;
-    const int nw = helper ? (int)nhelp * EP_WARPS : (int)nmain * EP_WARPS;
-    const int gtid = blockIdx.x * EP_THREADS + threadIdx.x, nthreads = (int)nmain * EP_THREADS;
+    const unsigned nblocks = gridDim.x;
     unsigned tgt_all = 0, tgt_main = 0, tgt_help = 0;
     unsigned *const bar_all = a.bar, *const bar_main = a.bar + 32, *const bar_help = a.bar + 64;
+
+    // Roles by SM: the CTAs of the first `main_sms` SMs run the phases of a step (MAIN), the others prepare the next
+    // step (HELPERS).  A main warp's phase is a few hundred instructions around one or two dependent memory round
+    // trips; sharing a scheduler with helper warps (long ready-to-issue sqrt / division chains) stretched every one
+    // of them, and both code paths fought over the instruction cache.  Every CTA takes a number within its role;
+    // the counts are read after a barrier, so nothing is assumed about how the hardware numbers or fills SMs.
+    __shared__ int s_role[2];
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const int r = (a.num_helpers > 0 && (int)smid >= a.main_sms) ? 1 : 0;
+        s_role[0] = r;
+        s_role[1] = atomicAdd(a.counts + 8 + r, 1);
+    }
+    grid_barrier(bar_all, tgt_all, nblocks);             // (__syncthreads inside publishes s_role)
+    unsigned nmain = (unsigned)__ldcg(a.counts + 8), nhelp = (unsigned)__ldcg(a.counts + 9);
+    bool helper = s_role[0] != 0;
+    int cidx = s_role[1];
+    if (a.num_helpers > 0 && (nmain == 0 || nhelp == 0)) {   // unexpected SM numbering: roles by block index
+        nhelp = (unsigned)a.num_helpers;
+        nmain = nblocks - nhelp;
+        helper = blockIdx.x >= nmain;
+        cidx = helper ? (int)(blockIdx.x - nmain) : (int)blockIdx.x;
+    }
+    // main: consecutive tasks (the parts of a long row, the long rows of the most active users) go to
+    // different CTAs -- with gw = cta * warps + warp the slowest CTA set the pace of every phase
+    const int gw = helper ? cidx * EP_WARPS + (int)(threadIdx.x >> 5) : (int)(threadIdx.x >> 5) * (int)nmain + cidx;
+    const int nw = helper ? (int)nhelp * EP_WARPS : (int)nmain * EP_WARPS;
+    const int gtid_all = blockIdx.x * EP_THREADS + threadIdx.x, nthreads_all = (int)nblocks * EP_THREADS;
+    const int gtid = helper ? -1 : cidx * EP_THREADS + (int)threadIdx.x;       // 0: the main CTAs' lead thread
+    const int htid = helper ? cidx * EP_THREADS + (int)threadIdx.x : -1, nhthreads = (int)nhelp * EP_THREADS;
     const int K = a.K, U = a.num_users;
     const size_t n = (size_t)a.num_users + (size_t)a.num_items;
     const Tab w{a.user_w, a.item_w, U};
     const float c0 = 1.0f / (float)((K + 1) * (K + 1));
-    float *const y0 = a.grad;                               // dead until the last backward layer writes grad
     float *const Z0 = a.work, *const Z1 = a.work + n * D;   // backward tables (the forward's y tables are dead then)
     float4 *const G4 = reinterpret_cast<float4 *>(a.G);
     const float4 *const F4 = reinterpret_cast<const float4 *>(a.final_emb);
     const long long t0 = *a.step;                           // only rewritten after the first barrier of a step
+
+    // Pull a step's launch-immutable arrays into L2 (two steps ahead of their use by the main CTAs' cache fill).
+    auto prefetch_step = [&](int s_, int tid, int nth) {
+        const StepDesc nx = a.steps[s_];
+        prefetch_range(nx.in_tasks, sizeof(lgcn_task) * (size_t)nx.n_in_tasks, tid, nth);
+        prefetch_range(nx.out_tasks, sizeof(lgcn_task) * (size_t)nx.n_out_tasks, tid, nth);
+        prefetch_range(nx.in_nbr, 4 * (size_t)nx.num_edges, tid, nth);
+        prefetch_range(nx.out_nbr, 4 * (size_t)nx.num_edges, tid, nth);
+        prefetch_range(nx.in_trip, 4 * (size_t)nx.num_edges, tid, nth);
+        prefetch_range(nx.out_trip, 4 * (size_t)nx.num_edges, tid, nth);
+        prefetch_range(nx.neg, 8 * (size_t)nx.P, tid, nth);
+        prefetch_range(nx.dis, 4 * n, tid, nth);
+    };
+#ifdef EP_TRACE
+    if (g_trace_smid && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_trace_smid[blockIdx.x] = (int)smid;
+        g_trace_smid[gridDim.x + blockIdx.x] = (helper ? 65536 : 0) + cidx;
+    }
+#endif
+    prefetch_step(0, gtid_all, nthreads_all);
+    if (a.num_steps > 1) prefetch_step(1, gtid_all, nthreads_all);
 
     // Prepare step s (number ts = t0+1+s): stamp its active rows, list its distinct inactive negatives, bring
     // both row sets to step ts-1.  Rows touched by the previous step are skipped (has_prev).  Executed by the
@@ -370,23 +616,38 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
         int32_t *list_s = a.neg_list + (size_t)par * a.num_items, *cnt_s = a.counts + par;
         const int32_t *act_p = s_ > 0 ? a.act_stamp + (size_t)(par ^ 1) * n : nullptr;
         const int32_t *flag_p = s_ > 0 ? a.neg_flag + (size_t)(par ^ 1) * a.num_items : nullptr;
-        if (pgw == 0 && lane == 0) *cnt_s = 0;
+        int32_t *const q_act = a.counts + 4, *const q_list = a.counts + 5;     // work queues, zero between uses
+        const int tb = s_ > 0 ? s_ - 1 : 0, ts0 = s_ > 0 ? 10 : 16;              // (trace slots of the diagnostic build)
+        if (pgw == 0 && lane == 0) { *cnt_s = 0; *q_list = 0; }
         replay_rows(RP_ACTIVE, sd.in_tasks, nullptr, sd.n_in_tasks, ts - 1, w, a.m, a.v, a.row_step, act_s, act_p, flag_p, a.h,
-                    pgw, pnw, lane);
-        grid_barrier(pbar, ptgt, pcount);
+                    pgw, pnw, lane, q_act);
+        grid_barrier(pbar, ptgt, pcount, tb, ts0);
+        if (pgw == 0 && lane == 0) *q_act = 0;                                    // everybody has left the queue
         for (long long base = (long long)pgw * 32; base < sd.P; base += (long long)pnw * 32) {
             const long long tt = base + lane;
+            bool add = false;
+            int i = 0;
             if (tt < sd.P) {
-                const int i = (int)__ldg(sd.neg + tt);
-                if (__ldcg(act_s + U + i) != ts && atomicExch(flag_s + i, ts) != ts) list_s[atomicAdd(cnt_s, 1)] = i;
+                i = (int)__ldg(sd.neg + tt);
+                add = __ldcg(act_s + U + i) != ts && atomicExch(flag_s + i, ts) != ts;
+            }
+            const unsigned mk = __ballot_sync(FULL, add);                         // one counter update per warp
+            if (mk) {
+                const int leader = __ffs(mk) - 1;
+                int pos = 0;
+                if (lane == leader) pos = atomicAdd(cnt_s, __popc(mk));
+                pos = __shfl_sync(FULL, pos, leader);
+                if (add) list_s[pos + __popc(mk & ((1u << lane) - 1u))] = i;
             }
         }
-        grid_barrier(pbar, ptgt, pcount);
+        grid_barrier(pbar, ptgt, pcount, tb, ts0 + 1);
         replay_rows(RP_LIST, nullptr, list_s, __ldcg(cnt_s), ts - 1, w, a.m, a.v, a.row_step, nullptr, act_p, flag_p, a.h, pgw,
-                    pnw, lane);
+                    pnw, lane, q_list);
     };
     prepare(0, gw_all, nw_all, bar_all, tgt_all, nblocks);
-    grid_barrier(bar_all, tgt_all, nblocks);
+    barrier_arrive(bar_all);
+    if (!helper) fill_cache(wc, a.steps[0], gw, nw, lane, U);
+    barrier_wait(bar_all, tgt_all, nblocks);
 
     for (int b = 0; b < a.num_steps; ++b) {
         const StepDesc d = a.steps[b];
@@ -403,32 +664,30 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
         const int32_t *const list_cur = a.neg_list + (size_t)par * a.num_items;
 
         if (helper) {
+            int hs = 12;
+            stamp(a.prof, b, hs, htid);
+            if (b + 2 < a.num_steps) prefetch_step(b + 2, htid, nhthreads);
             if (b + 1 < a.num_steps) prepare(b + 1, gw, nw, bar_help, tgt_help, nhelp);
-            grid_barrier(bar_all, tgt_all, nblocks);     // end of the step
+            stamp(a.prof, b, hs, htid);
+            grid_barrier(bar_all, tgt_all, nblocks, b, 2 * K + 3);     // end of the step
             continue;
         }
-
-        // ---- A: y0 = dis (.) e0 for the active rows (already at step t-1) ------------------------
-        if (gtid == 0) {
+        if (gtid == 0) {                                 // the other parity's sums: last read in step b-1, next used in b+1
             double *nx = a.accum + ((b + 1) & 1) * 4;
             nx[0] = 0.0; nx[1] = 0.0; nx[2] = 0.0; nx[3] = 0.0;
         }
-        for (int ti = gw * 2 + half; ti < d.n_in_tasks; ti += nw * 2) {
-            const int4 ta = __ldg(reinterpret_cast<const int4 *>(d.in_tasks + ti));
-            const int4 tc = __ldg(reinterpret_cast<const int4 *>(d.in_tasks + ti) + 1);
-            if (tc.x == 0)
-                reinterpret_cast<float4 *>(y0)[(size_t)ta.x * D4 + l16] = f4scale(dis_of(tc.z), ldcg4(w.row4(ta.x) + l16));
-        }
-        grid_barrier(bar_main, tgt_main, nmain);
-        stamp(a.prof, b, ps, gtid);
 
-        // ---- B: forward layers 1..K --------------------------------------------------------------
+        // ---- B: forward layers 1..K (layer 1 reads the weight tables of the active rows: all at step t-1) ----
         auto fwd_layer = [&](int k) {
-            const float *src = k == 1 ? y0 : a.work + (size_t)(k - 2) * n * D;
+            const float *src = k == 1 ? nullptr : a.work + (size_t)(k - 2) * n * D;
             float *dst = a.work + (size_t)(k - 1) * n * D;
             const bool last = k == K;
-            run_tasks(d.in_tasks, 0, d.n_in_tasks, d.partials, d.slot_counters, gw, nw, lane,
-                      [&](int, int begin, int end, float4 &acc, float &) { gather_sum(d.in_nbr, src, begin, end, lane, acc); },
+            run_tasks(wc, DIR_IN, d.in_tasks, 0, d.n_in_tasks, d.partials, d.slot_counters, gw, nw, lane,
+                      [&](int, int begin, int end, int cs, float4 &acc, float &) {
+                          const int32_t *cn = cs >= 0 ? wc.nbr[DIR_IN][cs] : nullptr;
+                          if (k == 1) gather_sum_e0(d.in_nbr, d.dis, cn, cs >= 0 ? wc.wgt[cs] : nullptr, w, begin, end, lane, acc);
+                          else gather_sum(d.in_nbr, cn, src, begin, end, lane, acc);
+                      },
                       [&](int row, int din, int, const float4 &raw, float) {
                           if (!last) {
                               const float inv = din > 0 ? 1.0f / (float)din : 0.f;
@@ -449,14 +708,14 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
         };
         for (int k = 1; k <= K; ++k) {
             fwd_layer(k);
-            grid_barrier(bar_main, tgt_main, nmain);
+            grid_barrier(bar_main, tgt_main, nmain, b, ps);
             stamp(a.prof, b, ps, gtid);
         }
 
         // ---- E: BPR over user rows -------------------------------------------------------------
         float ex0 = 0.f, ex1 = 0.f;
-        run_tasks(d.out_tasks, 0, d.n_out_user_tasks, d.partials, d.slot_counters, gw, nw, lane,
-                  [&](int row, int begin, int end, float4 &acc, float &sc) {
+        run_tasks(wc, DIR_OUT, d.out_tasks, 0, d.n_out_user_tasks, d.partials, d.slot_counters, gw, nw, lane,
+                  [&](int row, int begin, int end, int cs, float4 &acc, float &sc) {
                       const float ru = __ldcg(a.rnorm + row);
                       const float4 fu = f4scale(ru, ldcg4(F4 + (size_t)row * D4 + l16));
                       float loss = 0.f;
@@ -467,12 +726,20 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                               it.dst = -1; it.t = 0; it.ng = 0; it.rp = 0.f; it.rn = 0.f;
                               it.vp = f4zero(); it.vn = f4zero();
                               if (e >= 0) {
-                                  it.dst = __ldg(d.out_nbr + e);
-                                  it.t = __ldg(d.out_trip + e);
-                                  it.ng = (int)__ldg(d.neg + it.t) + U;
+                                  if (cs >= 0) {
+                                      it.dst = wc.nbr[DIR_OUT][cs][e - begin];
+                                      it.t = wc.trip[DIR_OUT][cs][e - begin];
+                                      it.ng = wc.ng[cs][e - begin];
+                                  } else {
+                                      it.dst = __ldg(d.out_nbr + e);
+                                      it.t = __ldg(d.out_trip + e);
+                                      it.ng = (int)__ldg(d.neg + it.t) + U;
+                                  }
+                                  // three independent loads: rnorm of an inactive negative is stale and not used
                                   it.rp = __ldcg(a.rnorm + it.dst);
-                                  if (__ldcg(act_cur + it.ng) != t) it.rn = -1.f;      // inactive: formed below
-                                  else it.rn = __ldcg(a.rnorm + it.ng);
+                                  const int st_ng = __ldcg(act_cur + it.ng);
+                                  const float rn_ng = __ldcg(a.rnorm + it.ng);
+                                  it.rn = st_ng != t ? -1.f : rn_ng;                    // inactive: formed below
                               }
                               return it;
                           },
@@ -521,22 +788,26 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                           reinterpret_cast<float4 *>(Z1)[(size_t)row * D4 + l16] = f4scale(dis_of(din), g);
                       }
                   });
-        if (lane == 0 && ex0 != 0.f) atomicAdd(acc_cur + 0, (double)ex0);
-        grid_barrier(bar_main, tgt_main, nmain);
+        cta_add2(s_red, lane, ex0, 0.f, acc_cur + 0, nullptr);
+        grid_barrier(bar_main, tgt_main, nmain, b, ps);
         stamp(a.prof, b, ps, gtid);
 
         // ---- F: BPR over item rows -------------------------------------------------------------
-        run_tasks(d.in_tasks, d.n_in_user_tasks, d.n_in_tasks, d.partials, d.slot_counters, gw, nw, lane,
-                  [&](int, int begin, int end, float4 &acc, float &sc) {
+        run_tasks(wc, DIR_IN, d.in_tasks, d.n_in_user_tasks, d.n_in_tasks, d.partials, d.slot_counters, gw, nw, lane,
+                  [&](int, int begin, int end, int cs, float4 &acc, float &sc) {
                       for_each_edge_rolled<TripB, EP_BPR_B_UNROLL>(
                           begin, end, lane,
                           [&](int e) {
                               TripB it;
                               it.u = -1; it.s = 0.f; it.scp = 0.f; it.ru = 0.f; it.vu = f4zero();
-                              if (e >= 0) it.u = __ldg(d.in_nbr + e);
+                              int tr = -1;
+                              if (e >= 0) {
+                                  if (cs >= 0) { it.u = wc.nbr[DIR_IN][cs][e - begin]; tr = wc.trip[DIR_IN][cs][e - begin]; }
+                                  else { it.u = __ldg(d.in_nbr + e); tr = __ldg(d.in_trip + e); }
+                              }
                               if (it.u >= U) it.u = -1;
                               if (it.u >= 0) {
-                                  const float2 sc2 = __ldcg(reinterpret_cast<const float2 *>(a.scratch) + __ldg(d.in_trip + e));
+                                  const float2 sc2 = __ldcg(reinterpret_cast<const float2 *>(a.scratch) + tr);
                                   it.ru = __ldcg(a.rnorm + it.u);
                                   it.s = sc2.x * it.ru;
                                   it.scp = sc2.x * sc2.y;
@@ -565,8 +836,8 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
         // the INACTIVE negatives' gradient rows (nothing propagates to a row without edges): grad = G/(K+1)^2 + reg.
         // Their dL/dfinal rows and the histogram are complete since the barrier after E; this phase has only the
         // item rows' tasks, so the list fills otherwise idle warps.
+        float n0 = 0.f, n1 = 0.f;
         {
-            float n0 = 0.f, n1 = 0.f;
             const int cnt = __ldcg(cnt_cur);
             for (int base = gw * 2; base < cnt; base += nw * 2) {
                 const int idx = base + half;
@@ -587,10 +858,9 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                 n1 += warp_sum(f4dot(g, g));
                 n0 += warp_sum(reg);
             }
-            if (lane == 0 && n0 != 0.f) atomicAdd(acc_cur + 1, (double)n0);
-            if (lane == 0 && n1 != 0.f) atomicAdd(acc_cur + 2, (double)n1);
         }
-        grid_barrier(bar_main, tgt_main, nmain);
+        cta_add2(s_red, lane, n0, n1, acc_cur + 1, acc_cur + 2);
+        grid_barrier(bar_main, tgt_main, nmain, b, ps);
         stamp(a.prof, b, ps, gtid);
 
         // ---- G: backward layers 1..K (Horner) ------------------------------------------------------
@@ -599,8 +869,10 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
             const float *src = (j & 1) ? Z1 : Z0;
             float *dst = (j & 1) ? Z0 : Z1;
             const bool last = j == K;
-            run_tasks(d.out_tasks, 0, d.n_out_tasks, d.partials, d.slot_counters, gw, nw, lane,
-                      [&](int, int begin, int end, float4 &acc, float &) { gather_sum(d.out_nbr, src, begin, end, lane, acc); },
+            run_tasks(wc, DIR_OUT, d.out_tasks, 0, d.n_out_tasks, d.partials, d.slot_counters, gw, nw, lane,
+                      [&](int, int begin, int end, int cs, float4 &acc, float &) {
+                          gather_sum(d.out_nbr, cs >= 0 ? wc.nbr[DIR_OUT][cs] : nullptr, src, begin, end, lane, acc);
+                      },
                       [&](int row, int din, int dout, const float4 &S, float) {
                           const float dd = dis_of(din);
                           float4 hh = ldcg4(G4 + (size_t)row * D4 + l16);
@@ -617,26 +889,23 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                               ex1 += half_sum(f4dot(g, g));
                           }
                       });
-            if (last) {
-                if (lane == 0 && ex0 != 0.f) atomicAdd(acc_cur + 1, (double)ex0);
-                if (lane == 0 && ex1 != 0.f) atomicAdd(acc_cur + 2, (double)ex1);
-            }
-            grid_barrier(bar_main, tgt_main, nmain);
-        stamp(a.prof, b, ps, gtid);
+            if (last) cta_add2(s_red, lane, ex0, ex1, acc_cur + 1, acc_cur + 2);
+            grid_barrier(bar_main, tgt_main, nmain, b, ps);
+            stamp(a.prof, b, ps, gtid);
         }
 
-        // ---- J: clip + Adam step t on the touched rows, loss, prefetch the next step -------------
+        // ---- J: clip + Adam step t on the touched rows, loss; then fetch the next step's work --------
         {
             const AdamScalars as = adam_scalars_tab(a.h, t);
             const float clip = clip_coef(a.h, __ldcg(acc_cur + 2));
             const float4 *gr = reinterpret_cast<const float4 *>(a.grad);
-            for (int base = gw * 2; base < d.n_in_tasks; base += nw * 2) {
-                const int ti = base + half;
-                if (ti < d.n_in_tasks) {
-                    const int4 ta = __ldg(reinterpret_cast<const int4 *>(d.in_tasks + ti));
-                    const int part = __ldg(&d.in_tasks[ti].part);
-                    if (part == 0) adam_row(ta.x, lane, t, w, a.m, a.v, gr, G4, a.row_step, a.neg_count, clip, as);
-                }
+            // one half-warp per active row, found through this warp's own in-tasks (first part speaks for the row)
+            int ci = half;
+            for (int ti = gw + half * nw; ti < d.n_in_tasks; ti += 2 * nw, ci += 2) {
+                int row, part;
+                if (ci < EP_CT) { row = wc.ta[DIR_IN][ci].x; part = wc.tc[DIR_IN][ci].x; }
+                else { row = __ldg(&d.in_tasks[ti].row); part = __ldg(&d.in_tasks[ti].part); }
+                if (part == 0) adam_row(row, lane, t, w, a.m, a.v, gr, G4, a.row_step, a.neg_count, clip, as);
             }
             const int cnt = __ldcg(cnt_cur);
             for (int idx = gw * 2 + half; idx < cnt; idx += nw * 2)
@@ -646,18 +915,11 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                 d.loss_out[0] = (float)(-__ldcg(acc_cur + 0) / (10.0 * p) + (double)a.bpr_coeff * __ldcg(acc_cur + 1) / (64.0 * p));
                 *a.step = (long long)t;
             }
-            if (b + 1 < a.num_steps) {
-                const StepDesc nx = a.steps[b + 1];
-                prefetch_range(nx.in_tasks, sizeof(lgcn_task) * (size_t)nx.n_in_tasks, gtid, nthreads);
-                prefetch_range(nx.out_tasks, sizeof(lgcn_task) * (size_t)nx.n_out_tasks, gtid, nthreads);
-                prefetch_range(nx.in_nbr, 4 * (size_t)nx.num_edges, gtid, nthreads);
-                prefetch_range(nx.out_nbr, 4 * (size_t)nx.num_edges, gtid, nthreads);
-                prefetch_range(nx.in_trip, 4 * (size_t)nx.num_edges, gtid, nthreads);
-                prefetch_range(nx.out_trip, 4 * (size_t)nx.num_edges, gtid, nthreads);
-                prefetch_range(nx.neg, 8 * (size_t)nx.P, gtid, nthreads);
-            }
         }
-        grid_barrier(bar_all, tgt_all, nblocks);
+        barrier_arrive(bar_all, b, ps);
+        if (b + 1 < a.num_steps) fill_cache(wc, a.steps[b + 1], gw, nw, lane, U);   // overlaps the wait
+        EP_TRACE_AT(b, ps + 1, 0);                                                   // cache filled
+        barrier_wait(bar_all, tgt_all, nblocks, b, ps);
         stamp(a.prof, b, ps, gtid);
     }
 }
@@ -701,11 +963,12 @@ extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_ste
         LGCN_REQUIRE(g.num_nodes == N && g.num_users == U, LGCN_E_INVALID, "train_steps_sparse: graph %lld has another shape",
                      (long long)b);
         LGCN_REQUIRE(g.num_triplets > 0, LGCN_E_INVALID, "train_steps_sparse: batch %lld has no user->movie edge", (long long)b);
-        LGCN_REQUIRE(g.in_tasks && g.out_tasks && g.partials && g.slot_counters, LGCN_E_INVALID,
+        LGCN_REQUIRE(g.in_tasks && g.out_tasks && g.partials && g.slot_counters && g.dis, LGCN_E_INVALID,
                      "train_steps_sparse: graph %lld not built", (long long)b);
         StepDesc &d = descs[(size_t)b];
         d.in_tasks = g.in_tasks; d.out_tasks = g.out_tasks;
         d.in_nbr = g.in_nbr; d.in_trip = g.in_trip; d.out_nbr = g.out_nbr; d.out_trip = g.out_trip;
+        d.dis = g.dis;
         d.partials = g.partials; d.slot_counters = g.slot_counters;
         d.neg = np; d.loss_out = loss_out + b; d.P = g.num_triplets;
         d.n_in_tasks = g.n_in_tasks; d.n_out_tasks = g.n_out_tasks;
@@ -734,7 +997,7 @@ extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_ste
     static const bool want_prof = getenv("LGCN_EPOCH_PROF") != nullptr;   // tools/epoch_breakdown.py
     a.prof = want_prof ? (long long *)(state + 512) : nullptr;
 
-    static int grid = 0;
+    static int grid = 0, num_sms = 0, ctas_per_sm = 0;
     if (grid == 0) {
         int dev = 0, sms = 0, per_sm = 0, coop = 0;
         LGCN_CUDA(cudaGetDevice(&dev));
@@ -743,12 +1006,30 @@ extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_ste
         LGCN_REQUIRE(coop, LGCN_E_CUDA, "train_steps_sparse: device does not support cooperative launches");
         LGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epoch_kernel, EP_THREADS, 0));
         LGCN_REQUIRE(per_sm >= 1, LGCN_E_CUDA, "train_steps_sparse: kernel does not fit on an SM");
-        grid = sms * (per_sm >= EP_CTAS_PER_SM ? EP_CTAS_PER_SM : per_sm);
+        num_sms = sms;
+        ctas_per_sm = per_sm >= EP_CTAS_PER_SM ? EP_CTAS_PER_SM : per_sm;
+        grid = sms * ctas_per_sm;                         // the cooperative launch fills every SM with ctas_per_sm CTAs
     }
-    static const int helpers_env = getenv("LGCN_EPOCH_HELPERS") ? atoi(getenv("LGCN_EPOCH_HELPERS")) : -1;   // tuning aid
-    a.num_helpers = num_steps > 1 ? (helpers_env >= 1 ? helpers_env : (grid * 9) / 20) : 0;
-    if (num_steps > 1 && a.num_helpers < 1) a.num_helpers = 1;
-    if (a.num_helpers > grid - 1) a.num_helpers = grid - 1;
+    // helpers: whole SMs (LGCN_EPOCH_HELPER_SMS: tuning aid)
+    static const int hsms_env = getenv("LGCN_EPOCH_HELPER_SMS") ? atoi(getenv("LGCN_EPOCH_HELPER_SMS")) : -1;
+    int helper_sms = hsms_env >= 1 ? hsms_env : (num_sms * 3) / 10;
+    if (helper_sms > num_sms - 1) helper_sms = num_sms - 1;
+    if (helper_sms < 1) helper_sms = 1;
+    a.num_helpers = num_steps > 1 && num_sms > 1 ? helper_sms * ctas_per_sm : 0;
+    a.main_sms = num_sms - helper_sms;
+#ifdef EP_TRACE
+    {
+        const char *tp = getenv("LGCN_EPOCH_TRACE_PTR");
+        long long *ptr = tp ? (long long *)strtoull(tp, nullptr, 0) : nullptr;
+        LGCN_CUDA(cudaMemcpyToSymbolAsync(g_trace, &ptr, sizeof(ptr), 0, cudaMemcpyHostToDevice, st));
+        const char *tw = getenv("LGCN_EPOCH_TRACE_WARP_PTR");
+        long long *wptr = tw ? (long long *)strtoull(tw, nullptr, 0) : nullptr;
+        LGCN_CUDA(cudaMemcpyToSymbolAsync(g_trace_warp, &wptr, sizeof(wptr), 0, cudaMemcpyHostToDevice, st));
+        const char *tsm = getenv("LGCN_EPOCH_TRACE_SMID_PTR");
+        int *sptr = tsm ? (int *)strtoull(tsm, nullptr, 0) : nullptr;
+        LGCN_CUDA(cudaMemcpyToSymbolAsync(g_trace_smid, &sptr, sizeof(sptr), 0, cudaMemcpyHostToDevice, st));
+    }
+#endif
     void *params[] = {(void *)&a};
     LGCN_CUDA(cudaLaunchCooperativeKernel((const void *)epoch_kernel, dim3(grid), dim3(EP_THREADS), params, 0, st));
     return LGCN_OK;
