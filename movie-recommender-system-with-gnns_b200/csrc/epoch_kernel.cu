@@ -48,9 +48,6 @@ namespace ep {
 #ifndef EP_BPR_A_UNROLL
 #define EP_BPR_A_UNROLL 2
 #endif
-#ifndef EP_BPR_B_UNROLL
-#define EP_BPR_B_UNROLL 4
-#endif
 #ifndef EP_CTAS_PER_SM
 #define EP_CTAS_PER_SM 3
 #endif
@@ -109,7 +106,8 @@ __device__ __forceinline__ void stamp(long long *prof, int b, int &slot, int gti
 // Diagnostic build (tools/epoch_trace.py): every CTA records when it arrives at and when it leaves each barrier.
 __device__ long long *g_trace;            // [num_steps][16][gridDim.x][2]
 __device__ long long *g_trace_warp;       // [num_steps][16][gridDim.x][8]: when each WARP reached the barrier
-__device__ int *g_trace_smid;             // [gridDim.x]
+__device__ int *g_trace_smid;             // [2][gridDim.x]: SM, role << 16 | index within the role
+__device__ long long *g_trace_fine;       // [num_steps][16][main warps (<= 4096)][8]: clock64 at points inside a phase
 __device__ __forceinline__ long long gtimer() {
     long long now;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
@@ -125,9 +123,15 @@ __device__ __forceinline__ long long gtimer() {
         if (g_trace_warp && (threadIdx.x & 31) == 0 && (slot) < 16)                                     \
             g_trace_warp[(((size_t)(b) * 16 + (slot)) * gridDim.x + blockIdx.x) * 8 + (threadIdx.x >> 5)] = gtimer(); \
     } while (0)
+#define EP_FINE(b, slot, gw, point)                                                                     \
+    do {                                                                                                \
+        if (g_trace_fine && (threadIdx.x & 31) == 0 && (slot) < 16 && (gw) < 4096)                      \
+            g_trace_fine[(((size_t)(b) * 16 + (slot)) * 4096 + (gw)) * 8 + (point)] = clock64();         \
+    } while (0)
 #else
 #define EP_TRACE_AT(b, slot, which) do { } while (0)
 #define EP_TRACE_WARP(b, slot) do { } while (0)
+#define EP_FINE(b, slot, gw, point) do { } while (0)
 #endif
 
 // Arrive (release) on a monotonic counter, wait (acquire) until `count` more CTAs have arrived than at
@@ -190,40 +194,18 @@ __device__ __forceinline__ void cta_add2(float (*red)[2], int lane, float v0, fl
 // immutable for the launch.  Tasks beyond EP_CT per warp, or longer than EP_CE edges, use the global path.
 constexpr int EP_CT = 2;
 constexpr int EP_CE = LGCN_ROW_SPLIT_SMALL;
+constexpr int EP_SCRATCH = EP_CT;           // slot index of the staging area for everything that is not resident
 constexpr int DIR_IN = 0, DIR_OUT = 1;
 struct __align__(16) WarpCache {
-    int4 ta[2][EP_CT], tc[2][EP_CT];      // [direction][slot]: the lgcn_task
-    int32_t nbr[2][EP_CT][EP_CE];         // in: source ids; out: target ids
-    int32_t trip[2][EP_CT][EP_CE];        // in (item rows) / out (user rows): triplet number of the edge
-    int32_t ng[EP_CT][EP_CE];             // out, user rows: num_users + negative item of the triplet
-    float wgt[EP_CT][EP_CE];              // in: dis[source]  (layer 1 reads e0 itself, no pre-scaled table)
+    int4 ta[2][EP_CT], tc[2][EP_CT];          // [direction][slot]: the lgcn_task
+    int32_t nbr[2][EP_CT + 1][EP_CE];         // in: source ids; out: target ids
+    int32_t trip[2][EP_CT + 1][EP_CE];        // in (item rows) / out (user rows): triplet number of the edge
+    int32_t ng[EP_CT + 1][EP_CE];             // out, user rows: num_users + negative item of the triplet
+    float wgt[2][EP_CT + 1][EP_CE];           // dis[neighbour]: forward layer 1 reads e0 itself, backward layer 1 dL/dfinal
 };
 
-// for_each_edge (rowtask.cuh) with the 32-edge chunk loop left ROLLED: the persistent kernel holds every
-// phase's code at once, and sixteen inlined copies of each edge body made it 220 KB -- every phase then
-// started with instruction-cache misses.  Same traversal order, same arithmetic.
-template <class Item, int kUnroll, class Fetch, class Load, class Apply>
-__device__ __forceinline__ void for_each_edge_rolled(int begin, int end, int lane, Fetch fetch, Load load, Apply apply) {
-    const int half = lane >> 4;
-    Item mine = fetch(begin + lane < end ? begin + lane : -1);
-    for (int base = begin; base < end; base += 32) {
-        const int n = min(32, end - base);
-        const int nb = base + 32 + lane;
-        Item next = fetch(nb < end ? nb : -1);
-#pragma unroll 1
-        for (int j = 0; j < n; j += 2 * kUnroll) {
-            Item it[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                it[u] = mine.shfl(j + 2 * u + half);
-                load(u, it[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) apply(u, it[u]);
-        }
-        mine = next;
-    }
-}
+// What a phase needs staged besides the neighbour ids when a chunk is not resident.
+enum { ST_NONE = 0, ST_WGT = 1, ST_TRIP = 2, ST_NG = 4 };
 
 struct Tab {                        // mutable e0 = (user_w, item_w)
     float *user, *item;
@@ -234,69 +216,82 @@ struct Tab {                        // mutable e0 = (user_w, item_w)
     }
 };
 
+__device__ __forceinline__ float dis_of(int deg_in) { return deg_in > 0 ? 1.0f / sqrtf((float)deg_in) : 0.f; }
+
+// Edges [0,n) of a chunk whose index runs sit in shared memory.  Half-warp h takes edges h, h+2, ...; kUnroll
+// edges per half-warp are in flight.  `fetch(e)` (e = -1 past the end) is evaluated by all 16 lanes of the half
+// (shared-memory broadcasts and same-address global loads), so no shuffle is needed to hand an edge to its lanes --
+// the shuffle-broadcast traversal of rowtask.cuh cost ~1400 cycles for a four-edge row here, against 310 for the
+// one L2 round trip in it.  The loop is rolled: the kernel holds every phase's code at once.
+template <class Item, int kUnroll, class Fetch, class Load, class Apply>
+__device__ __forceinline__ void for_each_edge_smem(int n, int half, Fetch fetch, Load load, Apply apply) {
+#pragma unroll 1
+    for (int o = 0; o < n; o += 2 * kUnroll) {
+        Item it[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int e = o + 2 * u + half;
+            it[u] = fetch(e < n ? e : -1);
+            load(u, it[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) apply(u, it[u]);
+    }
+}
+
 struct Nbr {
     int nbr;
     float w;
     float4 v;
-    __device__ __forceinline__ Nbr shfl(int src_lane) const {
-        Nbr r;
-        r.nbr = __shfl_sync(FULL, nbr, src_lane);
-        r.w = __shfl_sync(FULL, w, src_lane);
-        r.v = f4zero();
-        return r;
-    }
 };
 
-__device__ __forceinline__ float dis_of(int deg_in) { return deg_in > 0 ? 1.0f / sqrtf((float)deg_in) : 0.f; }
-
-// raw[c] = sum over the task's edges of x[nbr]   (x written earlier in this launch -> ld.cg).
-// c_nbr != null: the task's index run sits in shared memory (WarpCache), else nbr + begin.. in global memory.
-__device__ __noinline__ void gather_sum(const int32_t *__restrict__ nbr, const int32_t *c_nbr, const float *x, int begin,
-                                           int end, int lane, float4 &acc) {
-    const int l16 = lane & 15;
-    const float4 *x4 = reinterpret_cast<const float4 *>(x);
-    for_each_edge_rolled<Nbr, EP_GATHER_UNROLL>(
-        begin, end, lane,
-        [&](int e) {
-            Nbr it;
-            it.nbr = e >= 0 ? (c_nbr ? c_nbr[e - begin] : __ldg(nbr + e)) : -1;
-            it.w = 0.f;
-            it.v = f4zero();
-            return it;
-        },
-        [&](int, Nbr &it) { if (it.nbr >= 0) it.v = ldcg4(x4 + (size_t)it.nbr * D4 + l16); },
-        [&](int, Nbr &it) { f4add(acc, it.v); });
-}
-
-// Layer 1: raw[c] = sum dis[r] * e0[r] straight from the weight tables (the arithmetic of rowtask_kernel<FwdOp>'s
-// first layer: the scale rides in the fma), so no pre-scaled copy of the active rows is written first.
-__device__ __noinline__ void gather_sum_e0(const int32_t *__restrict__ nbr, const float *__restrict__ dis,
-                                              const int32_t *c_nbr, const float *c_wgt, const Tab &w, int begin, int end,
-                                              int lane, float4 &acc) {
-    const int l16 = lane & 15;
-    for_each_edge_rolled<Nbr, EP_GATHER_UNROLL>(
-        begin, end, lane,
-        [&](int e) {
-            Nbr it;
-            it.nbr = -1; it.w = 0.f; it.v = f4zero();
-            if (e >= 0) {
-                if (c_nbr) { it.nbr = c_nbr[e - begin]; it.w = c_wgt[e - begin]; }
-                else { it.nbr = __ldg(nbr + e); it.w = __ldg(dis + it.nbr); }
-            }
-            return it;
-        },
-        [&](int, Nbr &it) { if (it.nbr >= 0) it.v = ldcg4(w.row4(it.nbr) + l16); },
-        [&](int, Nbr &it) { f4fma(acc, it.w, it.v); });
+// Stage edges [e0, e0+n) (n <= EP_CE) of a task into the warp's scratch slot.
+struct StepDesc;
+template <int kNeed>
+__device__ __forceinline__ void stage_chunk(WarpCache &wc, int dir, const int32_t *__restrict__ nbr,
+                                            const int32_t *__restrict__ trp, const float *__restrict__ dis,
+                                            const int64_t *__restrict__ neg, int e0, int n, int lane, int U) {
+    int nb[EP_CE / 32], tr[EP_CE / 32];
+#pragma unroll
+    for (int h = 0; h < EP_CE / 32; ++h) {
+        const int e = lane + 32 * h;
+        nb[h] = e < n ? __ldg(nbr + e0 + e) : -1;
+        tr[h] = (kNeed & (ST_TRIP | ST_NG)) && e < n ? __ldg(trp + e0 + e) : -1;
+    }
+    float wg[EP_CE / 32];
+    int ngv[EP_CE / 32];
+#pragma unroll
+    for (int h = 0; h < EP_CE / 32; ++h) {
+        wg[h] = (kNeed & ST_WGT) && nb[h] >= 0 ? __ldg(dis + nb[h]) : 0.f;
+        ngv[h] = (kNeed & ST_NG) && tr[h] >= 0 ? U + (int)__ldg(neg + tr[h]) : 0;
+    }
+    __syncwarp();                                     // the slot may still be read by lanes of the previous chunk
+#pragma unroll
+    for (int h = 0; h < EP_CE / 32; ++h) {
+        const int e = lane + 32 * h;
+        wc.nbr[dir][EP_SCRATCH][e] = nb[h];
+        if (kNeed & (ST_TRIP | ST_NG)) wc.trip[dir][EP_SCRATCH][e] = tr[h];
+        if (kNeed & ST_WGT) wc.wgt[dir][EP_SCRATCH][e] = wg[h];
+        if (kNeed & ST_NG) wc.ng[EP_SCRATCH][e] = ngv[h];
+    }
+    __syncwarp();
 }
 
 // Walk the tasks [tb,te) of one list that belong to this warp (t = gw, gw + nw, ...: the same ownership in
 // every phase, which is what makes the WarpCache valid); same split-row protocol as rowtask_kernel.
-// accumulate(row, begin, end, cs, acc, sc): cs = cache slot holding the task's index runs, or -1.
-template <class Acc, class Epi>
-__device__ __forceinline__ void run_tasks(const WarpCache &wc, int dir, const lgcn_task *__restrict__ tasks, int tb, int te,
-                                          float *partials, int *counters, int gw, int nw, int lane, Acc accumulate,
-                                          Epi epilogue) {
+// accumulate(row, n, s, acc, sc): edges [0,n) of cache slot s.  A task that is not resident (beyond EP_CT per
+// warp, or longer than EP_CE edges) goes through the scratch slot in chunks of EP_CE edges, staged with what
+// the phase needs (kNeed); the traversal itself is the same.  kSc: the phase uses the per-row scalar.
+template <int kNeed, bool kSc, class Acc, class Epi>
+__device__ __forceinline__ void run_tasks(WarpCache &wc, int dir, const StepDesc &d, int tb, int te, int gw, int nw, int lane,
+                                          int U, Acc accumulate, Epi epilogue, int fb = 0, int fslot = 16) {
+    const lgcn_task *__restrict__ tasks = dir == DIR_IN ? d.in_tasks : d.out_tasks;
+    const int32_t *__restrict__ nbr = dir == DIR_IN ? d.in_nbr : d.out_nbr;
+    const int32_t *__restrict__ trp = dir == DIR_IN ? d.in_trip : d.out_trip;
+    float *const partials = d.partials;
+    int *const counters = d.slot_counters;
     int ci = 0;
+    EP_FINE(fb, fslot, gw, 0);
     for (int t = gw; t < te; t += nw, ++ci) {
         if (t < tb) continue;
         int4 ta, tc;
@@ -308,17 +303,26 @@ __device__ __forceinline__ void run_tasks(const WarpCache &wc, int dir, const lg
             tc = __ldg(reinterpret_cast<const int4 *>(tasks + t) + 1);
         }
         const int row = ta.x, begin = ta.y, end = ta.z, slot = ta.w, part = tc.x, nparts = tc.y;
-        const int cs = (ci < EP_CT && end - begin <= EP_CE) ? ci : -1;
+        const bool resident = ci < EP_CT && end - begin <= EP_CE;
         float4 acc = f4zero();
         float sc = 0.f;
-        accumulate(row, begin, end, cs, acc, sc);
+        if (ci == 0) EP_FINE(fb, fslot, gw, 1);
+        int e0 = begin;
+        do {
+            const int n = resident ? end - begin : min(EP_CE, end - e0);
+            if (!resident) stage_chunk<kNeed>(wc, dir, nbr, trp, d.dis, d.neg, e0, n, lane, U);
+            accumulate(row, n, resident ? ci : EP_SCRATCH, acc, sc);
+            e0 += EP_CE;
+        } while (!resident && e0 < end);
+        if (ci == 0) EP_FINE(fb, fslot, gw, 2);
         f4add(acc, f4shfl_xor16(acc));
-        sc = warp_sum(sc);
+        if (kSc) sc = warp_sum(sc);
+        if (ci == 0) EP_FINE(fb, fslot, gw, 3);
         bool run = slot < 0;
         if (slot >= 0) {
             float *p = partials + (size_t)slot * PARTIAL_STRIDE;
             if (lane < 16) reinterpret_cast<float4 *>(p)[lane] = acc;
-            if (lane == 16) p[D] = sc;
+            if (kSc && lane == 16) p[D] = sc;
             __threadfence();
             const int first = slot - part;
             int old = 0;
@@ -336,7 +340,7 @@ __device__ __forceinline__ void run_tasks(const WarpCache &wc, int dir, const lg
                     for (int u = 0; u < 4; ++u) {
                         const float *q = partials + (size_t)(first + min(i + u, nparts - 1)) * PARTIAL_STRIDE;
                         q4[u] = __ldcg(reinterpret_cast<const float4 *>(q) + (lane & 15));
-                        qs[u] = __ldcg(q + D);
+                        qs[u] = kSc ? __ldcg(q + D) : 0.f;
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
@@ -347,7 +351,9 @@ __device__ __forceinline__ void run_tasks(const WarpCache &wc, int dir, const lg
             }
         }
         if (run) epilogue(row, tc.z, tc.w, acc, sc);
+        if (ci == 0) EP_FINE(fb, fslot, gw, 4);
     }
+    EP_FINE(fb, fslot, gw, 5);
 }
 
 // Fill this warp's cache for the step described by d (launch-immutable data only; called between the arrive
@@ -378,8 +384,8 @@ __device__ __forceinline__ void fill_cache(WarpCache &wc, const StepDesc &d, int
 #pragma unroll
         for (int ci = 0; ci < EP_CT; ++ci) {
             const int begin = ta[dir][ci].y, len = ta[dir][ci].z - begin;
-            // triplet numbers: BPR walks the item rows of the by-target list and the user rows of the by-source list
-            const bool want_trip = dir == DIR_IN ? ta[dir][ci].x >= U : ta[dir][ci].x < U;
+            // triplet numbers: BPR walks the user rows of the by-source list
+            const bool want_trip = dir == DIR_OUT && ta[dir][ci].x < U;
 #pragma unroll
             for (int h = 0; h < EP_CE / 32; ++h) {
                 const int e = lane + 32 * h;
@@ -394,8 +400,9 @@ __device__ __forceinline__ void fill_cache(WarpCache &wc, const StepDesc &d, int
 #pragma unroll
         for (int h = 0; h < EP_CE / 32; ++h) {
             const int e = lane + 32 * h;
-            const int src = nb[DIR_IN][ci][h], t_out = tr[DIR_OUT][ci][h];
-            wc.wgt[ci][e] = src >= 0 ? __ldg(d.dis + src) : 0.f;
+            const int src = nb[DIR_IN][ci][h], dst = nb[DIR_OUT][ci][h], t_out = tr[DIR_OUT][ci][h];
+            wc.wgt[DIR_IN][ci][e] = src >= 0 ? __ldg(d.dis + src) : 0.f;
+            wc.wgt[DIR_OUT][ci][e] = dst >= 0 ? __ldg(d.dis + dst) : 0.f;
             wc.ng[ci][e] = t_out >= 0 ? U + (int)__ldg(d.neg + t_out) : 0;
         }
     }
@@ -407,7 +414,7 @@ __device__ __forceinline__ void fill_cache(WarpCache &wc, const StepDesc &d, int
 #pragma unroll
             for (int h = 0; h < EP_CE / 32; ++h) {
                 wc.nbr[dir][ci][lane + 32 * h] = nb[dir][ci][h];
-                wc.trip[dir][ci][lane + 32 * h] = tr[dir][ci][h];
+                if (dir == DIR_OUT) wc.trip[dir][ci][lane + 32 * h] = tr[dir][ci][h];
             }
         }
     __syncwarp();
@@ -515,21 +522,6 @@ struct TripA {
         r.rn = __shfl_sync(FULL, rn, src);
         r.vp = f4zero();
         r.vn = f4zero();
-        return r;
-    }
-};
-
-struct TripB {
-    int u;
-    float s, scp, ru;
-    float4 vu;
-    __device__ __forceinline__ TripB shfl(int src) const {
-        TripB r;
-        r.u = __shfl_sync(FULL, u, src);
-        r.s = __shfl_sync(FULL, s, src);
-        r.scp = __shfl_sync(FULL, scp, src);
-        r.ru = __shfl_sync(FULL, ru, src);
-        r.vu = f4zero();
         return r;
     }
 };
@@ -669,7 +661,7 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
             if (b + 2 < a.num_steps) prefetch_step(b + 2, htid, nhthreads);
             if (b + 1 < a.num_steps) prepare(b + 1, gw, nw, bar_help, tgt_help, nhelp);
             stamp(a.prof, b, hs, htid);
-            grid_barrier(bar_all, tgt_all, nblocks, b, 2 * K + 3);     // end of the step
+            grid_barrier(bar_all, tgt_all, nblocks, b, 2 * K + 2);     // end of the step
             continue;
         }
         if (gtid == 0) {                                 // the other parity's sums: last read in step b-1, next used in b+1
@@ -682,11 +674,24 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
             const float *src = k == 1 ? nullptr : a.work + (size_t)(k - 2) * n * D;
             float *dst = a.work + (size_t)(k - 1) * n * D;
             const bool last = k == K;
-            run_tasks(wc, DIR_IN, d.in_tasks, 0, d.n_in_tasks, d.partials, d.slot_counters, gw, nw, lane,
-                      [&](int, int begin, int end, int cs, float4 &acc, float &) {
-                          const int32_t *cn = cs >= 0 ? wc.nbr[DIR_IN][cs] : nullptr;
-                          if (k == 1) gather_sum_e0(d.in_nbr, d.dis, cn, cs >= 0 ? wc.wgt[cs] : nullptr, w, begin, end, lane, acc);
-                          else gather_sum(d.in_nbr, cn, src, begin, end, lane, acc);
+            run_tasks<ST_WGT, false>(wc, DIR_IN, d, 0, d.n_in_tasks, gw, nw, lane, U,
+                      [&](int, int n, int sl, float4 &acc, float &) {
+                          const int32_t *cn = wc.nbr[DIR_IN][sl];
+                          if (k == 1) {        // raw = sum dis[r] * e0[r] straight from the weight tables (no pre-scaled copy)
+                              const float *cw = wc.wgt[DIR_IN][sl];
+                              for_each_edge_smem<Nbr, EP_GATHER_UNROLL>(
+                                  n, half,
+                                  [&](int e) { Nbr it; it.nbr = e >= 0 ? cn[e] : -1; it.w = e >= 0 ? cw[e] : 0.f; it.v = f4zero(); return it; },
+                                  [&](int, Nbr &it) { if (it.nbr >= 0) it.v = ldcg4(w.row4(it.nbr) + l16); },
+                                  [&](int, Nbr &it) { f4fma(acc, it.w, it.v); });
+                          } else {
+                              const float4 *x4 = reinterpret_cast<const float4 *>(src);
+                              for_each_edge_smem<Nbr, EP_GATHER_UNROLL>(
+                                  n, half,
+                                  [&](int e) { Nbr it; it.nbr = e >= 0 ? cn[e] : -1; it.w = 0.f; it.v = f4zero(); return it; },
+                                  [&](int, Nbr &it) { if (it.nbr >= 0) it.v = ldcg4(x4 + (size_t)it.nbr * D4 + l16); },
+                                  [&](int, Nbr &it) { f4add(acc, it.v); });
+                          }
                       },
                       [&](int row, int din, int, const float4 &raw, float) {
                           if (!last) {
@@ -704,37 +709,33 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                               const float n2 = half_sum(f4dot(f, f));
                               if (lane == 0) a.rnorm[row] = 1.0f / sqrtf(n2);
                           }
-                      });
+                      }, b, ps);
         };
         for (int k = 1; k <= K; ++k) {
             fwd_layer(k);
+            EP_FINE(b, ps, gw, 6);
             grid_barrier(bar_main, tgt_main, nmain, b, ps);
+            EP_FINE(b, ps + 1, gw, 7);
             stamp(a.prof, b, ps, gtid);
         }
 
         // ---- E: BPR over user rows -------------------------------------------------------------
         float ex0 = 0.f, ex1 = 0.f;
-        run_tasks(wc, DIR_OUT, d.out_tasks, 0, d.n_out_user_tasks, d.partials, d.slot_counters, gw, nw, lane,
-                  [&](int row, int begin, int end, int cs, float4 &acc, float &sc) {
+        run_tasks<ST_TRIP | ST_NG, true>(wc, DIR_OUT, d, 0, d.n_out_user_tasks, gw, nw, lane, U,
+                  [&](int row, int n, int sl, float4 &acc, float &sc) {
                       const float ru = __ldcg(a.rnorm + row);
                       const float4 fu = f4scale(ru, ldcg4(F4 + (size_t)row * D4 + l16));
                       float loss = 0.f;
-                      for_each_edge_rolled<TripA, EP_BPR_A_UNROLL>(
-                          begin, end, lane,
+                      for_each_edge_smem<TripA, EP_BPR_A_UNROLL>(
+                          n, half,
                           [&](int e) {
                               TripA it;
                               it.dst = -1; it.t = 0; it.ng = 0; it.rp = 0.f; it.rn = 0.f;
                               it.vp = f4zero(); it.vn = f4zero();
                               if (e >= 0) {
-                                  if (cs >= 0) {
-                                      it.dst = wc.nbr[DIR_OUT][cs][e - begin];
-                                      it.t = wc.trip[DIR_OUT][cs][e - begin];
-                                      it.ng = wc.ng[cs][e - begin];
-                                  } else {
-                                      it.dst = __ldg(d.out_nbr + e);
-                                      it.t = __ldg(d.out_trip + e);
-                                      it.ng = (int)__ldg(d.neg + it.t) + U;
-                                  }
+                                  it.dst = wc.nbr[DIR_OUT][sl][e];
+                                  it.t = wc.trip[DIR_OUT][sl][e];
+                                  it.ng = wc.ng[sl][e];
                                   // three independent loads: rnorm of an inactive negative is stale and not used
                                   it.rp = __ldcg(a.rnorm + it.dst);
                                   const int st_ng = __ldcg(act_cur + it.ng);
@@ -765,9 +766,16 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                               if (valid) {
                                   if (l16 == 0) {
                                       sc += s * (cp - cn);
-                                      reinterpret_cast<float2 *>(a.scratch)[it.t] = make_float2(s, cp);
                                       atomicAdd(a.neg_count + (it.ng - U), 1);
                                   }
+                                  // dL/dfinal of both items of the triplet, added where they live: a cluster batch has at
+                                  // most a few dozen triplets per item, so the vector atomics do not pile up (the
+                                  // full-graph kernels walk the item rows instead, bpr.cu)
+                                  const float kp = s * it.rp * invP;
+                                  float4 gp = fu;
+                                  f4fma(gp, -cp * it.rp, it.vp);
+                                  gp = f4scale(kp, gp);
+                                  atomicAdd(G4 + (size_t)it.dst * D4 + l16, gp);
                                   const float kk = -s * it.rn * invP;
                                   float4 g = fu;
                                   f4fma(g, -cn * it.rn, it.vn);
@@ -783,95 +791,38 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                       float4 g = A;
                       f4fma(g, -B, fu);
                       g = f4scale(ru * invP, g);
-                      if (lane < 16) {
-                          G4[(size_t)row * D4 + l16] = g;
-                          reinterpret_cast<float4 *>(Z1)[(size_t)row * D4 + l16] = f4scale(dis_of(din), g);
-                      }
-                  });
+                      if (lane < 16) G4[(size_t)row * D4 + l16] = g;
+                  }, b, ps);
         cta_add2(s_red, lane, ex0, 0.f, acc_cur + 0, nullptr);
         grid_barrier(bar_main, tgt_main, nmain, b, ps);
         stamp(a.prof, b, ps, gtid);
 
-        // ---- F: BPR over item rows -------------------------------------------------------------
-        run_tasks(wc, DIR_IN, d.in_tasks, d.n_in_user_tasks, d.n_in_tasks, d.partials, d.slot_counters, gw, nw, lane,
-                  [&](int, int begin, int end, int cs, float4 &acc, float &sc) {
-                      for_each_edge_rolled<TripB, EP_BPR_B_UNROLL>(
-                          begin, end, lane,
-                          [&](int e) {
-                              TripB it;
-                              it.u = -1; it.s = 0.f; it.scp = 0.f; it.ru = 0.f; it.vu = f4zero();
-                              int tr = -1;
-                              if (e >= 0) {
-                                  if (cs >= 0) { it.u = wc.nbr[DIR_IN][cs][e - begin]; tr = wc.trip[DIR_IN][cs][e - begin]; }
-                                  else { it.u = __ldg(d.in_nbr + e); tr = __ldg(d.in_trip + e); }
-                              }
-                              if (it.u >= U) it.u = -1;
-                              if (it.u >= 0) {
-                                  const float2 sc2 = __ldcg(reinterpret_cast<const float2 *>(a.scratch) + tr);
-                                  it.ru = __ldcg(a.rnorm + it.u);
-                                  it.s = sc2.x * it.ru;
-                                  it.scp = sc2.x * sc2.y;
-                              }
-                              return it;
-                          },
-                          [&](int, TripB &it) { if (it.u >= 0) it.vu = ldcg4(F4 + (size_t)it.u * D4 + l16); },
-                          [&](int, TripB &it) {
-                              f4fma(acc, it.s, it.vu);
-                              if (l16 == 0) sc += it.scp;
-                          });
-                  },
-                  [&](int row, int din, int, const float4 &A, float B) {
-                      const float rp = __ldcg(a.rnorm + row);
-                      const float4 fp = f4scale(rp, ldcg4(F4 + (size_t)row * D4 + l16));
-                      float4 g = A;
-                      f4fma(g, -B, fp);
-                      g = f4scale(rp * invP, g);
-                      if (lane < 16) {
-                          float4 cur = ldcg4(G4 + (size_t)row * D4 + l16);      // negative-sample contributions (E)
-                          f4add(cur, g);
-                          G4[(size_t)row * D4 + l16] = cur;
-                          reinterpret_cast<float4 *>(Z1)[(size_t)row * D4 + l16] = f4scale(dis_of(din), cur);
-                      }
-                  });
-        // the INACTIVE negatives' gradient rows (nothing propagates to a row without edges): grad = G/(K+1)^2 + reg.
-        // Their dL/dfinal rows and the histogram are complete since the barrier after E; this phase has only the
-        // item rows' tasks, so the list fills otherwise idle warps.
-        float n0 = 0.f, n1 = 0.f;
-        {
-            const int cnt = __ldcg(cnt_cur);
-            for (int base = gw * 2; base < cnt; base += nw * 2) {
-                const int idx = base + half;
-                float4 g = f4zero();
-                float reg = 0.f;
-                if (idx < cnt) {
-                    const int item = __ldcg(list_cur + idx), row = U + item;
-                    g = f4scale(c0, ldcg4(G4 + (size_t)row * D4 + l16));
-                    G4[(size_t)row * D4 + l16] = f4zero();
-                    const int c = __ldcg(a.neg_count + item);
-                    if (c) {
-                        const float4 e = ldcg4(w.row4(row) + l16);
-                        f4fma(g, reg_coef * (float)c, e);
-                        reg = (float)c * f4dot(e, e);
-                    }
-                    reinterpret_cast<float4 *>(a.grad)[(size_t)row * D4 + l16] = g;
-                }
-                n1 += warp_sum(f4dot(g, g));
-                n0 += warp_sum(reg);
-            }
-        }
-        cta_add2(s_red, lane, n0, n1, acc_cur + 1, acc_cur + 2);
-        grid_barrier(bar_main, tgt_main, nmain, b, ps);
-        stamp(a.prof, b, ps, gtid);
-
         // ---- G: backward layers 1..K (Horner) ------------------------------------------------------
+        // Layer 1 gathers dL/dfinal itself with the weight dis[target] per edge (the item rows' dL/dfinal was summed by
+        // atomics in E, so there is no owner who could have written a pre-scaled copy); layers 2..K gather z = dis (.) h.
         ex0 = 0.f;
         for (int j = 1; j <= K; ++j) {
-            const float *src = (j & 1) ? Z1 : Z0;
+            const float *src = j == 1 ? a.G : ((j & 1) ? Z1 : Z0);
             float *dst = (j & 1) ? Z0 : Z1;
             const bool last = j == K;
-            run_tasks(wc, DIR_OUT, d.out_tasks, 0, d.n_out_tasks, d.partials, d.slot_counters, gw, nw, lane,
-                      [&](int, int begin, int end, int cs, float4 &acc, float &) {
-                          gather_sum(d.out_nbr, cs >= 0 ? wc.nbr[DIR_OUT][cs] : nullptr, src, begin, end, lane, acc);
+            run_tasks<ST_WGT, false>(wc, DIR_OUT, d, 0, d.n_out_tasks, gw, nw, lane, U,
+                      [&](int, int n, int sl, float4 &acc, float &) {
+                          const int32_t *cn = wc.nbr[DIR_OUT][sl];
+                          const float4 *x4 = reinterpret_cast<const float4 *>(src);
+                          if (j == 1) {
+                              const float *cw = wc.wgt[DIR_OUT][sl];
+                              for_each_edge_smem<Nbr, EP_GATHER_UNROLL>(
+                                  n, half,
+                                  [&](int e) { Nbr it; it.nbr = e >= 0 ? cn[e] : -1; it.w = e >= 0 ? cw[e] : 0.f; it.v = f4zero(); return it; },
+                                  [&](int, Nbr &it) { if (it.nbr >= 0) it.v = ldcg4(x4 + (size_t)it.nbr * D4 + l16); },
+                                  [&](int, Nbr &it) { f4fma(acc, it.w, it.v); });
+                          } else {
+                              for_each_edge_smem<Nbr, EP_GATHER_UNROLL>(
+                                  n, half,
+                                  [&](int e) { Nbr it; it.nbr = e >= 0 ? cn[e] : -1; it.w = 0.f; it.v = f4zero(); return it; },
+                                  [&](int, Nbr &it) { if (it.nbr >= 0) it.v = ldcg4(x4 + (size_t)it.nbr * D4 + l16); },
+                                  [&](int, Nbr &it) { f4add(acc, it.v); });
+                          }
                       },
                       [&](int row, int din, int dout, const float4 &S, float) {
                           const float dd = dis_of(din);
@@ -888,7 +839,31 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                               if (lane < 16) reinterpret_cast<float4 *>(a.grad)[(size_t)row * D4 + l16] = g;
                               ex1 += half_sum(f4dot(g, g));
                           }
-                      });
+                      }, b, ps);
+            if (j == 1) {
+                // the INACTIVE negatives' gradient rows (nothing propagates to a row without edges): grad = G/(K+1)^2 + reg.
+                // Their dL/dfinal rows and the histogram are complete since the barrier after E; no task gathers them.
+                const int cnt = __ldcg(cnt_cur);
+                for (int base = gw * 2; base < cnt; base += nw * 2) {
+                    const int idx = base + half;
+                    float4 g = f4zero();
+                    float reg = 0.f;
+                    if (idx < cnt) {
+                        const int item = __ldcg(list_cur + idx), row = U + item;
+                        g = f4scale(c0, ldcg4(G4 + (size_t)row * D4 + l16));
+                        G4[(size_t)row * D4 + l16] = f4zero();
+                        const int c = __ldcg(a.neg_count + item);
+                        if (c) {
+                            const float4 e = ldcg4(w.row4(row) + l16);
+                            f4fma(g, reg_coef * (float)c, e);
+                            reg = (float)c * f4dot(e, e);
+                        }
+                        reinterpret_cast<float4 *>(a.grad)[(size_t)row * D4 + l16] = g;
+                    }
+                    ex1 += warp_sum(f4dot(g, g));
+                    ex0 += warp_sum(reg);
+                }
+            }
             if (last) cta_add2(s_red, lane, ex0, ex1, acc_cur + 1, acc_cur + 2);
             grid_barrier(bar_main, tgt_main, nmain, b, ps);
             stamp(a.prof, b, ps, gtid);
@@ -1012,7 +987,7 @@ extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_ste
     }
     // helpers: whole SMs (LGCN_EPOCH_HELPER_SMS: tuning aid)
     static const int hsms_env = getenv("LGCN_EPOCH_HELPER_SMS") ? atoi(getenv("LGCN_EPOCH_HELPER_SMS")) : -1;
-    int helper_sms = hsms_env >= 1 ? hsms_env : (num_sms * 3) / 10;
+    int helper_sms = hsms_env >= 1 ? hsms_env : (num_sms * 7) / 20;
     if (helper_sms > num_sms - 1) helper_sms = num_sms - 1;
     if (helper_sms < 1) helper_sms = 1;
     a.num_helpers = num_steps > 1 && num_sms > 1 ? helper_sms * ctas_per_sm : 0;
@@ -1025,6 +1000,9 @@ extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_ste
         const char *tw = getenv("LGCN_EPOCH_TRACE_WARP_PTR");
         long long *wptr = tw ? (long long *)strtoull(tw, nullptr, 0) : nullptr;
         LGCN_CUDA(cudaMemcpyToSymbolAsync(g_trace_warp, &wptr, sizeof(wptr), 0, cudaMemcpyHostToDevice, st));
+        const char *tf = getenv("LGCN_EPOCH_TRACE_FINE_PTR");
+        long long *fptr = tf ? (long long *)strtoull(tf, nullptr, 0) : nullptr;
+        LGCN_CUDA(cudaMemcpyToSymbolAsync(g_trace_fine, &fptr, sizeof(fptr), 0, cudaMemcpyHostToDevice, st));
         const char *tsm = getenv("LGCN_EPOCH_TRACE_SMID_PTR");
         int *sptr = tsm ? (int *)strtoull(tsm, nullptr, 0) : nullptr;
         LGCN_CUDA(cudaMemcpyToSymbolAsync(g_trace_smid, &sptr, sizeof(sptr), 0, cudaMemcpyHostToDevice, st));

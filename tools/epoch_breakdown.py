@@ -57,18 +57,17 @@ if os.environ.get("LGCN_EPOCH_PROF"):
     ws = opt.buffers.steps_ws
     desc_bytes = L.lgcn_train_steps_workspace_bytes(nb) - 512 - 128 * nb
     prof = ws[desc_bytes + 512: desc_bytes + 512 + 128 * nb].view(torch.int64).view(nb, 16).cpu().numpy()
-    dur = np.diff(prof[:, :10], axis=1) / 1e3
-    names = ["fwd1 (reads e0)", "fwd2", "fwd3", "E bpr users", "F bpr items", "bwd1", "bwd2",
-             "bwd3+negs", "J adam+fill"]
+    dur = np.diff(prof[:, :9], axis=1) / 1e3
+    names = ["fwd1 (reads e0)", "fwd2", "fwd3", "E bpr (user rows)", "bwd1+negs", "bwd2", "bwd3", "J adam+fill"]
     print("per-phase us over %d steps (median / mean / max):" % nb)
     for i, nm in enumerate(names):
         print("  %-20s %7.1f %7.1f %7.1f" % (nm, np.median(dur[:, i]), dur[:, i].mean(), dur[:, i].max()))
-    tot = (prof[:, 9] - prof[:, 0]) / 1e3
+    tot = (prof[:, 8] - prof[:, 0]) / 1e3
     print("  step total           %7.1f %7.1f %7.1f   epoch kernel %.2f ms" % (np.median(tot), tot.mean(), tot.max(),
-                                                                               (prof[-1, 9] - prof[0, 0]) / 1e6))
+                                                                               (prof[-1, 8] - prof[0, 0]) / 1e6))
     hp = (prof[:-1, 13] - prof[:-1, 12]) / 1e3          # helper CTAs: prefetch + prepare of the next step
     print("  helpers (prepare)    %7.1f %7.1f %7.1f   steps where the helpers take longer than the main phases: %d"
-          % (np.median(hp), hp.mean(), hp.max(), int((prof[:-1, 13] > prof[:-1, 9 - 1] + 1000 * np.median(dur[:, 8])).sum())))
+          % (np.median(hp), hp.mean(), hp.max(), int((prof[:-1, 13] > prof[:-1, 7] + 1000 * np.median(dur[:, 7])).sum())))
 
 if os.environ.get("QUICK"):
     sys.exit(0)

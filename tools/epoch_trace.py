@@ -52,6 +52,8 @@ nb = len(parts)
 trace = torch.zeros(nb, 16, grid, 2, dtype=torch.int64, device=dev)
 wtrace = torch.zeros(nb, 16, grid, 8, dtype=torch.int64, device=dev)
 smid = torch.zeros(2 * grid, dtype=torch.int32, device=dev)
+fine = torch.zeros(nb, 16, 4096, 8, dtype=torch.int64, device=dev)
+os.environ["LGCN_EPOCH_TRACE_FINE_PTR"] = str(fine.data_ptr())
 os.environ["LGCN_EPOCH_TRACE_PTR"] = str(trace.data_ptr())
 os.environ["LGCN_EPOCH_TRACE_WARP_PTR"] = str(wtrace.data_ptr())
 os.environ["LGCN_EPOCH_TRACE_SMID_PTR"] = str(smid.data_ptr())
@@ -65,9 +67,8 @@ perm = np.concatenate([np.where(role == 0)[0][np.argsort(cidx[role == 0])], np.w
 nmain = int((role == 0).sum())
 nhelp = grid - nmain
 tr = tr[:, :, perm, :]
-last = 2 * K + 3                                            # slot of the end-of-step barrier
-names = {1: "fwd1", 2: "fwd2", 3: "fwd3", 4: "E bpr users", 5: "F bpr items", 6: "bwd1", 7: "bwd2", 8: "bwd3+negs",
-         9: "J adam (+fill)"}
+last = 2 * K + 2                                            # slot of the end-of-step barrier
+names = {1: "fwd1", 2: "fwd2", 3: "fwd3", 4: "E bpr (user rows)", 5: "bwd1+negs", 6: "bwd2", 7: "bwd3", 8: "J adam (+fill)"}
 print(f"grid {grid} CTAs: {nmain} main + {nhelp} helpers; {nb} steps; us, median over steps 1..{nb - 1}")
 print("%-16s %8s %8s %8s %8s | %8s %8s | %8s" % ("phase", "arr min", "arr med", "arr p90", "arr max", "rel first", "rel last", "phase"))
 tot = {}
@@ -152,3 +153,31 @@ for slot, lst in ((2, "in_tasks"), (6, "out_tasks")):
             if sel.any():
                 out.append("[%d..): n=%d med %.2f p99 %.2f" % (lo, sel.sum(), np.median(st[sel, 0]), np.percentile(st[sel, 0], 99)))
         print("   by %-22s %s" % (label, " | ".join(out)))
+
+# ---- clock64 stamps inside a forward phase (slot 2 = fwd2): cycles from the warp leaving the previous barrier ----
+fn = fine.cpu().numpy().astype(np.float64)
+rows = []
+for b in range(1, nb):
+    gr = model.graph(parts[b].edge_index)
+    nt = gr.c.n_in_tasks
+    if nt > 2 * nw:
+        continue
+    tk = gr.in_tasks.view(-1, 8).cpu().numpy()
+    ln = tk[:nt, 2] - tk[:nt, 1]
+    for gwi in range(min(nw, 4096)):
+        f = fn[b, 2, gwi]
+        if f[7] == 0 or f[0] == 0:
+            continue
+        ntask = len(ln[gwi:nt:nw])
+        first = ln[gwi] if gwi < nt else 0
+        base = f[7]                                       # left the barrier that ended fwd1
+        rows.append((ntask, first, f[0] - base, f[1] - base, f[2] - base, f[3] - base, f[4] - base, f[5] - base, f[6] - base))
+r = np.array(rows)
+print("fwd2, SM cycles after the warp left the previous barrier (median): enter run_tasks / descriptor read / gather done / "
+      "shuffles done / epilogue done / loop done / at barrier")
+for label, sel in (("no task", r[:, 0] == 0), ("1 task, <=4 edges", (r[:, 0] == 1) & (r[:, 1] <= 4)),
+                   ("1 task, 5-16 edges", (r[:, 0] == 1) & (r[:, 1] > 4) & (r[:, 1] <= 16)),
+                   ("1 task, 17-32", (r[:, 0] == 1) & (r[:, 1] > 16) & (r[:, 1] <= 32)),
+                   ("1 task, 33-64", (r[:, 0] == 1) & (r[:, 1] > 32)), ("2 tasks", r[:, 0] == 2)):
+    if sel.any():
+        print("   %-20s n=%6d  " % (label, sel.sum()) + "  ".join("%6.0f" % np.median(r[sel, i]) for i in range(2, 9)))
