@@ -45,8 +45,10 @@ extern "C" {
 
 #define LGCN_DIM 64
 #define LGCN_ROW_SPLIT 512          /* max edges handled by one warp task (large graphs)  */
+#ifndef LGCN_ROW_SPLIT_SMALL          /* (compile-time tuning knob of the library build) */
 #define LGCN_ROW_SPLIT_SMALL 64     /* same, for edge lists below LGCN_SMALL_GRAPH edges: the longest
                                        task is the critical path of a launch-sized Cluster-GCN batch */
+#endif
 #define LGCN_SMALL_GRAPH (1 << 20)
 
 #define LGCN_OK 0

@@ -144,7 +144,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
     if (threadIdx.x == 0) {
         unsigned cur;
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(bar), "r"(1u) : "memory");
-        do {
+        do {          // (relaxed polls + one acquire fence were measured: 0.25-0.5 us SLOWER per barrier)
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar) : "memory");
         } while ((int)(cur - target) < 0);
     }
@@ -164,7 +164,7 @@ __device__ __forceinline__ void barrier_wait(unsigned *bar, unsigned &target, un
     target += count;
     if (threadIdx.x == 0) {
         unsigned cur;
-        do {
+        do {          // (relaxed polls + one acquire fence were measured: 0.25-0.5 us SLOWER per barrier)
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar) : "memory");
         } while ((int)(cur - target) < 0);
     }
@@ -192,8 +192,14 @@ __device__ __forceinline__ void cta_add2(float (*red)[2], int lane, float v0, fl
 // fetched once per step (during the wait of the previous step's last barrier) instead of heading every
 // phase with a descriptor -> index -> row chain of dependent L2 round trips.  Everything cached is
 // immutable for the launch.  Tasks beyond EP_CT per warp, or longer than EP_CE edges, use the global path.
-constexpr int EP_CT = 2;
-constexpr int EP_CE = LGCN_ROW_SPLIT_SMALL;
+#ifndef EP_CACHE_TASKS
+#define EP_CACHE_TASKS 2
+#endif
+#ifndef EP_CACHE_EDGES
+#define EP_CACHE_EDGES 64
+#endif
+constexpr int EP_CT = EP_CACHE_TASKS;       // resident tasks per warp and direction
+constexpr int EP_CE = EP_CACHE_EDGES;       // edges per cache slot (a multiple of 32)
 constexpr int EP_SCRATCH = EP_CT;           // slot index of the staging area for everything that is not resident
 constexpr int DIR_IN = 0, DIR_OUT = 1;
 struct __align__(16) WarpCache {
@@ -486,6 +492,48 @@ __device__ __noinline__ void replay_rows(int mode, const lgcn_task *__restrict__
     }
 }
 
+// The list rows (inactive negatives) have short chains (an item is sampled every ~17 steps) and cold state, so a
+// row costs mostly its dependent loads: two rows per warp (half-warp / float4 layout, adam_replay_kernel's) halve
+// the number of rounds.  Same queue protocol as replay_rows, in pairs.
+__device__ __noinline__ void replay_list(const int32_t *list, int count, int target, Tab w, float4 *m, float4 *v,
+                                         int32_t *row_step, const int32_t *act_p, const int32_t *flag_p, AdamHyper h, int gw,
+                                         int nw, int lane, int32_t *queue) {
+    const int half = lane >> 4, l16 = lane & 15;
+    const unsigned half_mask = 0xffffu << (lane & 16);
+    int i = 2 * gw;
+    while (i < count) {                                               // warp-uniform
+        int nxt = 0;
+        if (lane == 0) nxt = 2 * nw + 2 * atomicAdd(queue, 1);
+        const int mine = i + half;
+        bool valid = mine < count;
+        int row = 0;
+        if (valid) {
+            row = w.num_users + __ldcg(list + mine);
+            valid = !touched_by(row, w.num_users, target, act_p, flag_p);
+        }
+        const int from = valid ? __ldcg(row_step + row) : target;
+        valid = valid && from < target;
+        float4 *pp = w.row4(row) + l16;
+        const size_t o = (size_t)row * D4 + l16;
+        float4 p4 = f4zero(), m4 = f4zero(), v4 = f4zero();
+        if (valid) { p4 = ldcg4(pp); m4 = ldcg4(m + o); v4 = ldcg4(v + o); }
+        const bool live = m4.x != 0.f || m4.y != 0.f || m4.z != 0.f || m4.w != 0.f ||
+                          v4.x != 0.f || v4.y != 0.f || v4.z != 0.f || v4.w != 0.f;
+        const bool any_live = (__ballot_sync(FULL, live) & half_mask) != 0u;
+        if (valid && any_live) {
+            const float4 zero = f4zero();
+#pragma unroll 2
+            for (int t = from + 1; t <= target; ++t) {
+                const AdamScalars a = adam_scalars_tab(h, t);
+                adam_vec(p4, m4, v4, zero, 1.0f, a);
+            }
+            *pp = p4; m[o] = m4; v[o] = v4;
+        }
+        if (valid && l16 == 0) row_step[row] = target;
+        i = __shfl_sync(FULL, nxt, 0);
+    }
+}
+
 __device__ __noinline__ void adam_row(int row, int lane, int t, const Tab &w, float4 *m, float4 *v, const float4 *grad,
                                          float4 *G, int32_t *row_step, int32_t *neg_count, float clip,
                                          const AdamScalars &a) {
@@ -633,8 +681,7 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
             }
         }
         grid_barrier(pbar, ptgt, pcount, tb, ts0 + 1);
-        replay_rows(RP_LIST, nullptr, list_s, __ldcg(cnt_s), ts - 1, w, a.m, a.v, a.row_step, nullptr, act_p, flag_p, a.h, pgw,
-                    pnw, lane, q_list);
+        replay_list(list_s, __ldcg(cnt_s), ts - 1, w, a.m, a.v, a.row_step, act_p, flag_p, a.h, pgw, pnw, lane, q_list);
     };
     prepare(0, gw_all, nw_all, bar_all, tgt_all, nblocks);
     barrier_arrive(bar_all);
@@ -721,10 +768,14 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
 
         // ---- E: BPR over user rows -------------------------------------------------------------
         float ex0 = 0.f, ex1 = 0.f;
+        float ru_row = 0.f;                 // 1/||final|| and normalised final row of the user this warp works on:
+        float4 fu_row = f4zero();           // loaded by accumulate, reused by the epilogue of the same row
         run_tasks<ST_TRIP | ST_NG, true>(wc, DIR_OUT, d, 0, d.n_out_user_tasks, gw, nw, lane, U,
                   [&](int row, int n, int sl, float4 &acc, float &sc) {
                       const float ru = __ldcg(a.rnorm + row);
                       const float4 fu = f4scale(ru, ldcg4(F4 + (size_t)row * D4 + l16));
+                      ru_row = ru;
+                      fu_row = fu;
                       float loss = 0.f;
                       for_each_edge_smem<TripA, EP_BPR_A_UNROLL>(
                           n, half,
@@ -785,12 +836,10 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                           });
                       ex0 += warp_sum(loss);
                   },
-                  [&](int row, int din, int, const float4 &A, float B) {
-                      const float ru = __ldcg(a.rnorm + row);
-                      const float4 fu = f4scale(ru, ldcg4(F4 + (size_t)row * D4 + l16));
+                  [&](int row, int, int, const float4 &A, float B) {
                       float4 g = A;
-                      f4fma(g, -B, fu);
-                      g = f4scale(ru * invP, g);
+                      f4fma(g, -B, fu_row);
+                      g = f4scale(ru_row * invP, g);
                       if (lane < 16) G4[(size_t)row * D4 + l16] = g;
                   }, b, ps);
         cta_add2(s_red, lane, ex0, 0.f, acc_cur + 0, nullptr);
@@ -850,11 +899,12 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                     float reg = 0.f;
                     if (idx < cnt) {
                         const int item = __ldcg(list_cur + idx), row = U + item;
-                        g = f4scale(c0, ldcg4(G4 + (size_t)row * D4 + l16));
-                        G4[(size_t)row * D4 + l16] = f4zero();
+                        const float4 gf = ldcg4(G4 + (size_t)row * D4 + l16);        // three independent loads
                         const int c = __ldcg(a.neg_count + item);
+                        const float4 e = ldcg4(w.row4(row) + l16);
+                        g = f4scale(c0, gf);
+                        G4[(size_t)row * D4 + l16] = f4zero();
                         if (c) {
-                            const float4 e = ldcg4(w.row4(row) + l16);
                             f4fma(g, reg_coef * (float)c, e);
                             reg = (float)c * f4dot(e, e);
                         }
