@@ -79,24 +79,18 @@ __global__ void fill_csr_kernel(const int *__restrict__ eid_sorted, const int *_
     trip[s] = row32[e] < U ? trip_scan[e] - trip_scan[__ldg(eoff + bid[e])] : -1;
 }
 
-// ptr[b][n] = first position (relative to the batch) whose sorted key is >= (b, n);  grid.y = batch
-__global__ void ptr_kernel(const key_t *__restrict__ keys_sorted, const long long *__restrict__ eoff, long long N,
-                           int nbits, int *__restrict__ ptr) {
-    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n > N) return;
-    const int b = blockIdx.y;
-    const long long e0 = __ldg(eoff + b), e1 = __ldg(eoff + b + 1);
-    long long lo = e0, hi = e1;
-    if (n < N) {
-        const key_t want = ((key_t)b << nbits) | (key_t)n;
-        while (lo < hi) {
-            const long long mid = (lo + hi) >> 1;
-            if (__ldg(keys_sorted + mid) < want) lo = mid + 1; else hi = mid;
-        }
-    } else {
-        lo = e1;
-    }
-    ptr[(long long)b * (N + 1) + n] = (int)(lo - e0);
+// ptr[b][n] = first position (relative to the batch) whose sorted key is >= (b, n), for all B x (N+1) cells: degree
+// histogram (one atomic per edge) + ONE exclusive scan over the whole grid.  The spare cell [b][N] of every row holds
+// -E_b, so the running sum is back to zero at the start of the next row and the scan yields batch-relative positions
+// directly.  (A bisection per cell took 0.3 ms per direction at 100 x 221,589 cells: 13 dependent loads each.)
+__global__ void degree_kernel(const key_t *__restrict__ keys_sorted, const long long *__restrict__ eoff, long long E,
+                              long long N, int B, int nbits, int *__restrict__ ptr) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < B) ptr[e * (N + 1) + N] = -(int)(__ldg(eoff + e + 1) - __ldg(eoff + e));
+    if (e >= E) return;
+    const key_t k = keys_sorted[e];
+    const long long b = (long long)(k >> nbits), n = (long long)(k & (((key_t)1 << nbits) - 1));
+    atomicAdd(ptr + b * (N + 1) + n, 1);
 }
 
 __global__ void node_kernel(const int *__restrict__ in_ptr, const int *__restrict__ out_ptr,
@@ -346,8 +340,13 @@ extern "C" int lgcn_graph_build_batched(const int64_t *edges, const int64_t *edg
             fill_csr_kernel<<<gE, T, 0, st>>>(w.eid_sorted, other, w.row32, w.trip_scan, w.bid, w.eoff, E, (int)U,
                                              dir == 0 ? a.in_nbr : a.out_nbr, dir == 0 ? a.in_trip : a.out_trip);
             LGCN_LAUNCH_CHECK();
-            ptr_kernel<<<gN, T, 0, st>>>(w.keys_sorted, w.eoff, N, nbits, dir == 0 ? a.in_ptr : a.out_ptr);
+            int *ptr = dir == 0 ? a.in_ptr : a.out_ptr;
+            const long long pcells = (long long)B * (N + 1);
+            LGCN_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int) * (size_t)pcells, st));
+            degree_kernel<<<cdiv((E > B ? E : B), T), T, 0, st>>>(w.keys_sorted, w.eoff, E, N, (int)B, nbits, ptr);
             LGCN_LAUNCH_CHECK();
+            tb = w.cub_bytes;
+            LGCN_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, ptr, ptr, (int)pcells, st));
         }
     } else {
         LGCN_CUDA(cudaMemsetAsync(a.in_ptr, 0, sizeof(int) * (size_t)B * (size_t)(N + 1), st));
