@@ -537,16 +537,22 @@ def run_c3(args):
 
     # e2e: edge list uploaded from pinned host memory, CSR rebuilt, one step, loss read back
     host_ei = train.pin_memory()
-    e2e_steps = 2
-    torch.cuda.synchronize(); trainer.comm.barrier()
-    a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
+    e2e_steps = max(2, min(args.steps, 5))
     from lgcn_b200 import _lib
-    for _ in range(e2e_steps):
+
+    def e2e_step():
         ei = host_ei.to(dev, non_blocking=True)
         fresh = _lib.Graph(ei, g.num_users, g.num_items)           # K0 on the uploaded edge list
         del fresh                                                   # (same content: the trainer keeps its CSR)
-        float(step().item())
+        return float(step().item())
+
+    for _ in range(2):                                              # untimed: the caching allocator gets its blocks
+        e2e_step()
+    torch.cuda.synchronize(); trainer.comm.barrier()
+    a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(e2e_steps):
+        e2e_step()
     z.record()
     torch.cuda.synchronize()
     te = torch.tensor([a.elapsed_time(z) / e2e_steps], dtype=torch.float64, device=dev)
