@@ -300,9 +300,36 @@ def run_c2(args):
            "spmm_full_graph": spmm,
            "setup_ms": {"cluster_extract": extract_ms, "graph_build_100_batches": build_ms},
            "final_epoch_loss": losses[-1]}
+    if args.workload == "c2" and not args.no_eval:
+        try:
+            out["full_graph_step_1gpu_c3"] = full_graph_step_single_gpu(g, k, dev)
+        except Exception as exc:                                    # an extra, never the reason for a missing line
+            out["full_graph_step_1gpu_c3"] = {"error": repr(exc)[:200]}
     if not args.no_cpu:
         out["cpu_baseline"] = run_cpu_arm(g, cluster_batches_cpu(train, cluster, n), k, 2, 1)
     return out
+
+
+def full_graph_step_single_gpu(g, k, dev, steps=10, warmup=3):
+    """The N > 1 workload (C3: one full-graph training step, node-range sharded) on ONE GPU, so that the per-N lines
+    of the scaling run can be set against a single-GPU run of the SAME workload (the N = 1 line itself is C2)."""
+    from lgcn_b200 import sharded
+    tr = g.edges("train").to(dev)
+    ops = sharded.CudaOps(tr, g.num_users, g.num_items, k)
+    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
+    trainer = sharded.ShardedTrainer(ops, u0.to(dev), i0.to(dev), sharded.Comm())
+    for _ in range(warmup):
+        trainer.step_sampled(g.num_items, use_graph=False)
+    torch.cuda.synchronize()
+    a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        trainer.step_sampled(g.num_items, use_graph=False)
+    z.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(z) / steps
+    return {"workload": "C3 full-graph training step on 1 GPU (what `--gpus N` runs sharded)", "ms_per_step": ms,
+            "edges_per_s": tr.shape[1] / (ms * 1e-3), "steps": steps, "warmup": warmup}
 
 
 def launches_per_step(k: int, sparse: bool) -> int:
