@@ -574,9 +574,52 @@ struct TripA {
     }
 };
 
+// BPR arithmetic of one triplet, evaluated by a half-warp that holds the three rows (utils/train_test.py:18-64 for one
+// (u, i+, i-)): fu = normalised user row, vp / vn = final rows of the items, rp = 1/||vp||, rn = 1/||vn|| or < 0 when
+// the negative is inactive in this batch (vn is then c0 * e0[neg] and its norm is formed here).
+struct BprOut {
+    float s, cp, cn, rn, sp;
+};
+__device__ __forceinline__ BprOut bpr_math(const float4 &fu, const float4 &vp, const float4 &vn, float rp, float rn) {
+    BprOut o;
+    const float n2 = half_sum(f4dot(vn, vn));
+    o.rn = rn < 0.f ? 1.0f / sqrtf(n2) : rn;
+    o.cp = half_sum(f4dot(fu, vp)) * rp;
+    o.cn = half_sum(f4dot(fu, vn)) * o.rn;
+    const float x = 10.f * (o.cp - o.cn);
+    o.sp = fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
+    o.s = -1.f / (1.f + expf(-x));
+    return o;
+}
+// dL/dfinal of both items of the triplet, added where they live: a cluster batch has at most a few dozen triplets per
+// item, so the vector atomics do not pile up (the full-graph kernels walk the item rows instead, bpr.cu)
+__device__ __forceinline__ void bpr_item_grads(float4 *G4, int dst, int ng, const float4 &fu, const float4 &vp,
+                                               const float4 &vn, float rp, const BprOut &o, float invP, int l16) {
+    const float kp = o.s * rp * invP;
+    float4 gp = fu;
+    f4fma(gp, -o.cp * rp, vp);
+    gp = f4scale(kp, gp);
+    atomicAdd(G4 + (size_t)dst * D4 + l16, gp);
+    const float kk = -o.s * o.rn * invP;
+    float4 g = fu;
+    f4fma(g, -o.cn * o.rn, vn);
+    g = f4scale(kk, g);
+    atomicAdd(G4 + (size_t)ng * D4 + l16, g);
+}
+
+struct TripP {                       // a pooled triplet: user row and accumulator slot travel with it
+    int row, dst, ng, j;
+    float ru, rp, rn;
+    float4 vu, vp, vn;
+};
+
+static_assert(EP_WARPS * EP_CT <= 16, "the pooled BPR pass scans the CTA's task slots with a half-warp");
+
 __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const EpochArgs a) {
     __shared__ WarpCache s_cache[EP_WARPS];
     __shared__ float s_red[EP_WARPS][2];
+    __shared__ __align__(16) float s_acc[EP_WARPS * EP_CT][D + 4];   // BPR: user-row sums of the CTA's resident tasks; [D] = the row scalar
+    __shared__ int s_cnt[16];
     WarpCache &wc = s_cache[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
     const int gw_all = blockIdx.x * EP_WARPS + (threadIdx.x >> 5), nw_all = gridDim.x * EP_WARPS;
@@ -767,15 +810,106 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
         }
 
         // ---- E: BPR over user rows -------------------------------------------------------------
+        // The triplets of the CTA's resident user tasks are POOLED: every half-warp takes triplets round-robin, whoever
+        // owns the user, and adds the user-row terms into shared-memory accumulators -- a user with many triplets no longer
+        // keeps one warp busy for several rounds while the rest of the CTA waits at the barrier.  The owner then runs the
+        // row epilogue.  Non-resident tasks (hub cluster) are walked by their owner as before.
         float ex0 = 0.f, ex1 = 0.f;
         float ru_row = 0.f;                 // 1/||final|| and normalised final row of the user this warp works on:
         float4 fu_row = f4zero();           // loaded by accumulate, reused by the epilogue of the same row
+        bool pooled = false;                // CTA-uniform: the resident user tasks went through the pooled pass
+        {
+            const int wid = threadIdx.x >> 5;
+            if (lane < EP_CT) {
+                const int4 ta = wc.ta[DIR_OUT][lane];
+                const int len = ta.z - ta.y;
+                s_cnt[wid * EP_CT + lane] = (gw + lane * nw < d.n_out_user_tasks && len <= EP_CE) ? len : 0;
+            }
+            for (int i = lane; i < EP_CT * (D + 4); i += 32) (&s_acc[wid * EP_CT][0])[i] = 0.f;
+            __syncthreads();
+            constexpr int NS = EP_WARPS * EP_CT;
+            const int cnt_l = l16 < NS ? s_cnt[l16] : 0;       // both halves scan the slots
+            int incl = cnt_l;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o, 16);
+                if (l16 >= o) incl += v;
+            }
+            // Pooling pays when it shortens the longest chain; with hundreds of triplets per CTA (hub cluster) every warp
+            // is busy anyway and the extra user-row load per triplet only costs.
+            const int total_all = __shfl_sync(FULL, incl, 15, 16);
+            pooled = total_all <= 16 * EP_BPR_A_UNROLL * 4;
+            const int total = pooled ? total_all : 0;
+            const int excl = incl - cnt_l;
+            const int hh = wid * 2 + half;
+            float loss = 0.f;
+#pragma unroll 1
+            for (int base = 0; base < total; base += 16 * EP_BPR_A_UNROLL) {       // CTA-uniform trip count
+                TripP it[EP_BPR_A_UNROLL];
+#pragma unroll
+                for (int u = 0; u < EP_BPR_A_UNROLL; ++u) {
+                    const int k = base + u * 16 + hh;
+                    const bool ok = k < total;
+                    // slot of pooled triplet k = number of slots whose inclusive prefix is <= k (empty slots drop out)
+                    const unsigned m = __ballot_sync(FULL, ok && l16 < NS && incl <= k);
+                    const int j = __popc((m >> (16 * half)) & 0xffffu);
+                    const int e = k - __shfl_sync(FULL, excl, j & 15, 16);
+                    TripP &q = it[u];
+                    q.row = 0; q.dst = -1; q.ng = 0; q.j = j & 15; q.ru = 0.f; q.rp = 0.f; q.rn = 0.f;
+                    q.vu = f4zero(); q.vp = f4zero(); q.vn = f4zero();
+                    if (ok) {
+                        const WarpCache &oc = s_cache[j / EP_CT];
+                        const int ci = j % EP_CT;
+                        q.row = oc.ta[DIR_OUT][ci].x;
+                        q.dst = oc.nbr[DIR_OUT][ci][e];
+                        q.ng = oc.ng[ci][e];
+                        q.ru = __ldcg(a.rnorm + q.row);
+                        q.rp = __ldcg(a.rnorm + q.dst);
+                        const int st_ng = __ldcg(act_cur + q.ng);
+                        const float rn_ng = __ldcg(a.rnorm + q.ng);
+                        q.rn = st_ng != t ? -1.f : rn_ng;                                // inactive: formed in bpr_math
+                        q.vu = ldcg4(F4 + (size_t)q.row * D4 + l16);
+                        q.vp = ldcg4(F4 + (size_t)q.dst * D4 + l16);
+                        if (q.rn < 0.f) q.vn = f4scale(c0, ldcg4(w.row4(q.ng) + l16));
+                        else q.vn = ldcg4(F4 + (size_t)q.ng * D4 + l16);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < EP_BPR_A_UNROLL; ++u) {
+                    TripP &q = it[u];
+                    const float4 fu = f4scale(q.ru, q.vu);
+                    const BprOut o = bpr_math(fu, q.vp, q.vn, q.rp, q.rn);
+                    if (q.dst >= 0) {
+                        float *sa = &s_acc[q.j][0];
+                        const float kp = o.s * q.rp, kn = -o.s * o.rn;
+                        atomicAdd(sa + 4 * l16 + 0, fmaf(kp, q.vp.x, kn * q.vn.x));
+                        atomicAdd(sa + 4 * l16 + 1, fmaf(kp, q.vp.y, kn * q.vn.y));
+                        atomicAdd(sa + 4 * l16 + 2, fmaf(kp, q.vp.z, kn * q.vn.z));
+                        atomicAdd(sa + 4 * l16 + 3, fmaf(kp, q.vp.w, kn * q.vn.w));
+                        if (l16 == 0) {
+                            loss += o.sp;
+                            atomicAdd(sa + D, o.s * (o.cp - o.cn));
+                            atomicAdd(a.neg_count + (q.ng - U), 1);
+                        }
+                        bpr_item_grads(G4, q.dst, q.ng, fu, q.vp, q.vn, q.rp, o, invP, l16);
+                    }
+                }
+            }
+            ex0 += warp_sum(loss);
+            __syncthreads();
+        }
         run_tasks<ST_TRIP | ST_NG, true>(wc, DIR_OUT, d, 0, d.n_out_user_tasks, gw, nw, lane, U,
                   [&](int row, int n, int sl, float4 &acc, float &sc) {
                       const float ru = __ldcg(a.rnorm + row);
                       const float4 fu = f4scale(ru, ldcg4(F4 + (size_t)row * D4 + l16));
                       ru_row = ru;
                       fu_row = fu;
+                      if (pooled && sl != EP_SCRATCH) { // resident: summed by the pooled pass (half 0 / lane 0 carry the value)
+                          const float *sa = &s_acc[(threadIdx.x >> 5) * EP_CT + sl][0];
+                          if (lane < 16) acc = *reinterpret_cast<const float4 *>(sa + 4 * l16);
+                          if (lane == 0) sc = sa[D];
+                          return;
+                      }
                       float loss = 0.f;
                       for_each_edge_smem<TripA, EP_BPR_A_UNROLL>(
                           n, half,
@@ -785,13 +919,12 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                               it.vp = f4zero(); it.vn = f4zero();
                               if (e >= 0) {
                                   it.dst = wc.nbr[DIR_OUT][sl][e];
-                                  it.t = wc.trip[DIR_OUT][sl][e];
                                   it.ng = wc.ng[sl][e];
                                   // three independent loads: rnorm of an inactive negative is stale and not used
                                   it.rp = __ldcg(a.rnorm + it.dst);
                                   const int st_ng = __ldcg(act_cur + it.ng);
                                   const float rn_ng = __ldcg(a.rnorm + it.ng);
-                                  it.rn = st_ng != t ? -1.f : rn_ng;                    // inactive: formed below
+                                  it.rn = st_ng != t ? -1.f : rn_ng;                    // inactive: formed in bpr_math
                               }
                               return it;
                           },
@@ -803,35 +936,16 @@ __global__ void __launch_bounds__(EP_THREADS, EP_CTAS_PER_SM) epoch_kernel(const
                               }
                           },
                           [&](int, TripA &it) {
-                              const bool valid = it.dst >= 0;
-                              const float n2 = half_sum(f4dot(it.vn, it.vn));
-                              if (it.rn < 0.f) it.rn = 1.0f / sqrtf(n2);
-                              const float cp = half_sum(f4dot(fu, it.vp)) * it.rp;
-                              const float cn = half_sum(f4dot(fu, it.vn)) * it.rn;
-                              const float x = 10.f * (cp - cn);
-                              const float sp = fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
-                              if (valid && l16 == 0) loss += sp;
-                              const float s = -1.f / (1.f + expf(-x));
-                              f4fma(acc, s * it.rp, it.vp);
-                              f4fma(acc, -s * it.rn, it.vn);
-                              if (valid) {
+                              const BprOut o = bpr_math(fu, it.vp, it.vn, it.rp, it.rn);
+                              f4fma(acc, o.s * it.rp, it.vp);
+                              f4fma(acc, -o.s * o.rn, it.vn);
+                              if (it.dst >= 0) {
                                   if (l16 == 0) {
-                                      sc += s * (cp - cn);
+                                      loss += o.sp;
+                                      sc += o.s * (o.cp - o.cn);
                                       atomicAdd(a.neg_count + (it.ng - U), 1);
                                   }
-                                  // dL/dfinal of both items of the triplet, added where they live: a cluster batch has at
-                                  // most a few dozen triplets per item, so the vector atomics do not pile up (the
-                                  // full-graph kernels walk the item rows instead, bpr.cu)
-                                  const float kp = s * it.rp * invP;
-                                  float4 gp = fu;
-                                  f4fma(gp, -cp * it.rp, it.vp);
-                                  gp = f4scale(kp, gp);
-                                  atomicAdd(G4 + (size_t)it.dst * D4 + l16, gp);
-                                  const float kk = -s * it.rn * invP;
-                                  float4 g = fu;
-                                  f4fma(g, -cn * it.rn, it.vn);
-                                  g = f4scale(kk, g);
-                                  atomicAdd(G4 + (size_t)it.ng * D4 + l16, g);
+                                  bpr_item_grads(G4, it.dst, it.ng, fu, it.vp, it.vn, it.rp, o, invP, l16);
                               }
                           });
                       ex0 += warp_sum(loss);
