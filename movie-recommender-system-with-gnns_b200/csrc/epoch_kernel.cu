@@ -6,34 +6,43 @@
 // a batch touches are visited, the zero-gradient Adam updates of the others are replayed exactly when
 // they are next touched.
 //
-// Why one kernel: a median ML-25M cluster batch has 2.2 k active rows and 7 k edges; as 16 launches
-// per step the epoch is bound by launch/drain latency and by dependent COLD misses (task -> index ->
-// row), ~185 us per step measured.  Here one CTA per SM stays resident for the whole run, phases are
-// separated by device-wide barriers, per-node metadata rides in the task descriptors (deg_in /
-// deg_out) so no O(N) array is touched, layer 1 gathers a PRE-SCALED table (no per-edge normalisation
-// gather), and the next step's descriptors and index arrays are prefetched into L2.
+// Why one kernel: a median ML-25M cluster batch has 2.1 k active rows, 6.8 k edges and 3.4 k triplets; as 16
+// launches per step the epoch is bound by launch/drain latency, ~185 us per step measured.  Here three CTAs per SM
+// stay resident for the whole run and phases are separated by device-wide barriers.  What a phase costs is not
+// memory (one L2 round trip of a 256-byte row is 310 cycles) but the chain of dependent instructions every warp
+// of an SM runs at the same moment, so the design keeps that chain short:
+//   * per-node metadata rides in the task descriptors (deg_in / deg_out): no O(N) array is touched;
+//   * each warp keeps a shared-memory image of its tasks (WarpCache: descriptors, neighbour ids, per-edge
+//     weights dis[nbr], triplet / negative ids), fetched once per step while the previous step's last barrier
+//     is waited for; phases read indices by shared-memory broadcast (no shuffle, no descriptor -> index ->
+//     row chain of dependent loads);
+//   * layer 1 reads the weight tables with the per-edge weight (no pre-scaled table, no pre-scale phase).
 //
-// Two CTA roles.  The replay of pending zero-gradient Adam steps is a long SEQUENTIAL chain per row (a
-// user row is touched once per epoch: ~100 steps, each with an IEEE sqrt and two divisions per element;
-// ~20 us for one warp) -- the same arithmetic dense Adam performs, but on the critical path if done when
-// the row is needed.  So:
-//   HELPER CTAs work one step AHEAD: during step b they prepare step b+1 -- stamp its active rows,
-//     collect its distinct inactive negatives (the run's negatives are sampled up front), and bring all
-//     those rows up to date, except rows step b touches itself (phase J leaves them up to date).
+// Two CTA roles, taken per SM (so the two instruction streams do not share schedulers or instruction cache).
+// The replay of pending zero-gradient Adam steps is a long SEQUENTIAL chain per row (a user row waits ~50
+// steps, each a sqrt and two divisions per element) -- the same arithmetic dense Adam performs, but on the
+// critical path if done when the row is needed.  So:
+//   HELPER CTAs work one step AHEAD: during step b they prepare step b+1 -- stamp its active rows, collect
+//     its distinct inactive negatives (the run's negatives are sampled up front), bring all those rows up to
+//     date (rows step b touches itself are skipped: phase J leaves them up to date), and prefetch step b+2's
+//     arrays into L2.
 //   MAIN CTAs run the phases of step b, separated by barriers among themselves:
-//     A  y0 = dis (.) e0 for the active rows                                                    |
-//     B  forward layers 1..K (barrier after each; the last forms the layer mean and 1/||.||)    |
-//     E  BPR over user rows (loss, user-row gradient, negative-item gradient by vector atomics) |
-//     F  BPR over item rows (positive-item gradient, owner computes); both write dis (.) G too;
-//        + the gradient rows of the inactive negatives                                          |
-//     G  backward layers 1..K (barrier after each)                                              |
-//     J  clip + Adam step on the touched rows, restore the all-zero invariants, loss, prefetch
+//     B  forward layers 1..K (barrier after each; the last forms the layer mean and 1/||.||)
+//     E  BPR: the CTA's half-warps share the triplets of its resident user tasks (user-row sums in shared
+//        memory, gradient of BOTH items by vector atomics), the owner runs the row epilogue
+//     G  backward layers 1..K (barrier after each); layer 1 gathers dL/dfinal with the weight dis[target]
+//        and also forms the gradient rows of the inactive negatives
+//     J  clip + Adam step on the touched rows, restore the all-zero invariants, loss; then fill the
+//        WarpCache for step b+1 between the arrive and the wait of the end-of-step barrier
 //   Everybody meets at the end of the step.  Step 0 is prepared by all CTAs before the loop.
 // Stamp / list arrays are double-buffered by step parity so that preparing b+1 never disturbs b.
 //
 // Memory rules inside the kernel: everything another SM may have written earlier in the launch is read
 // with ld.global.cg (L2, the coherence point); __ldg only for data that is immutable for the whole
-// launch (task lists, index arrays, negatives, the bias-correction table).
+// launch (task lists, index arrays, negatives, dis, the bias-correction table).
+//
+// Diagnostics: -DEP_TRACE builds the per-CTA / per-warp barrier trace (tools/epoch_trace.py); LGCN_EPOCH_PROF=1
+// makes the shipped kernel write one globaltimer stamp per phase (tools/epoch_breakdown.py).
 #include "adam.cuh"
 #include "rowtask.cuh"
 #include <stdlib.h>
