@@ -217,7 +217,11 @@ int lgcn_step_begin(const lgcn_adam *opt, double *accum, void *stream);
 
 /* grad scaled by min(1, max_norm / (sqrt(accum[2]) + 1e-6)), then torch.optim.Adam's update
  * on both tables.  Also writes loss = -accum[0]/(10 P) + bpr_coeff/(64 P) * accum[1] to
- * loss_out[0] if loss_out != null. */
+ * loss_out[0] if loss_out != null.
+ * Arithmetic: torch's formula and scalar handling (bias corrections in double, one cast to fp32); the square
+ * root and the two divisions per element use the hardware approximations (<= 1 / 2 ulp), so an update differs
+ * from torch's correctly rounded one by <= ~6e-10 at lr = 1e-3.  All Adam entry points (dense, row lists, the
+ * replay of deferred steps) share this arithmetic and are bit-identical to each other. */
 int lgcn_clip_adam(const lgcn_adam *opt, float *user_w, float *item_w, int64_t num_users,
                    int64_t num_items, const float *grad, const double *accum,
                    int64_t num_triplets, float bpr_coeff, float *loss_out, void *stream);
