@@ -273,6 +273,7 @@ def run_c2(args):
     roofline_step = {"kernel": "epoch_kernel (lgcn_train_steps_sparse: all sparse steps of an epoch in one launch)",
                      "bound": "hbm", "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "algorithmic_bytes_per_launch": step_bytes, "avg_launch_ms": ms_per_step,
+                     "traffic": ncu_traffic("epoch_kernel"),
                      "note": "latency-bound by construction: ~2 k rows and ~7 k edges per step, 2K+2 device-wide barriers "
                              "per step (see profiles/r1c_epoch_trace.txt for where a step goes); duration here is the whole "
                              "epoch (kernel + end-of-epoch flush)"}
