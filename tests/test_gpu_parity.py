@@ -397,8 +397,8 @@ def test_persistent_steps_kernel_equals_sequential_sparse_steps_and_oracle(shape
     l1, l2 = torch.cat(l1).cpu(), torch.cat(l2).cpu()
     assert float((l1 - l2).abs().max()) < 2e-6 * float(l2.abs().max())
     steps = epochs * len(batches)
-    # the persistent kernel gathers pre-scaled tables (dis (.) x rounded once) where the per-step kernels
-    # fuse the scale into an fma: gradient noise ~1e-10, amplified by Adam like any other (tests/conftest.py)
+    # the persistent kernel sums the BPR gradients of a batch in another order than the per-step kernels (pooled
+    # triplets, item rows by atomics): gradient noise ~1e-10, amplified by Adam like any other (tests/conftest.py)
     assert max_abs(m1.user_embedding.weight, m2.user_embedding.weight) < steps * ADAM_STEP_ATOL
     assert max_abs(m1.item_embedding.weight, m2.item_embedding.weight) < steps * ADAM_STEP_ATOL
     assert normwise(o1.exp_avg, o2.exp_avg) < 1e-4 and normwise(o1.exp_avg_sq, o2.exp_avg_sq) < 1e-4
