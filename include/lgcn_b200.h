@@ -249,12 +249,28 @@ typedef struct lgcn_peers {
  * Orders the peer / multicast stores of the preceding kernels before the following ones. */
 int lgcn_peer_barrier(const lgcn_peers *peers, int32_t *flags_local, int32_t *epoch, void *stream);
 
+/* Sum of accum[0..3] (doubles, device) over the ranks, in rank order, in place; also a barrier like lgcn_peer_barrier
+ * (same flag array and epoch).  slots_local = this rank's double[8*4] slot table inside the symmetric region.
+ * Replaces the all-reduce of the loss / clip sums (utils/train_test.py:95: clip_grad_norm_ needs the GLOBAL norm). */
+int lgcn_peer_allreduce4(const lgcn_peers *peers, int32_t *flags_local, int32_t *epoch, double *slots_local,
+                         double *accum, void *stream);
+
 int lgcn_prescale(const lgcn_graph *g, const float *user_w, const float *item_w, int64_t row_begin,
                   int64_t row_end, float *y0, const lgcn_peers *peers, void *stream);
 int lgcn_fwd_layer(const lgcn_graph *g, const float *user_w, const float *item_w, int k, int num_layers,
                    const float *yin, float *yout, const float *y1, const float *y2, const float *y3,
                    float *final_out, float *rnorm, int task_begin, int task_end, int64_t row_begin,
                    int64_t row_end, const lgcn_peers *peers, void *stream);
+/* lgcn_fwd_layer with flags.  LGCN_FWD_NORMALIZED (last layer only): final_out receives the L2-NORMALISED final rows
+ * final / ||final|| (every rank's copy) and rnorm[row] = 1 / ||final[row]|| is stored LOCALLY only -- the form
+ * lgcn_bpr_owner consumes (cosines become plain dot products, utils/train_test.py:53-64 applied once per row). */
+#define LGCN_FWD_NORMALIZED 1
+int lgcn_fwd_layer_ex(const lgcn_graph *g, const float *user_w, const float *item_w, int k, int num_layers,
+                      const float *yin, float *yout, const float *y1, const float *y2, const float *y3,
+                      float *final_out, float *rnorm, int task_begin, int task_end, int64_t row_begin,
+                      int64_t row_end, int flags, const lgcn_peers *peers, void *stream);
+/* j == 1: zin may be the pre-scaled table z_0 = dis (.) grad_final (what lgcn_bpr_owner stores as zG); NULL: the layer
+ * gathers grad_final itself and applies dis per edge. */
 int lgcn_bwd_layer(const lgcn_graph *g, const float *grad_final, int j, int num_layers, const float *zin,
                    float *zout, const float *user_w, const float *item_w, const int32_t *neg_count,
                    float reg_coef, float *grad_e0, double *accum, int task_begin, int task_end,
@@ -266,6 +282,46 @@ int lgcn_bpr_fwd_bwd_range(const lgcn_graph *g, const float *final_emb, const fl
                            const int64_t *neg, float *grad_final, int32_t *neg_count,
                            float *trip_scratch, double *accum, int user_task_begin, int user_task_end,
                            int64_t user_row_begin, int64_t user_row_end, void *stream);
+/* ---- owner-computes BPR (full-graph step, any world size) ------------------------------------------
+ * lgcn_bpr_fwd_bwd with every row of dL/dfinal produced by ONE warp task (no float atomics, bit-stable):
+ * the triplets' negatives are bucketed by item each step, user rows / item rows are walked by their owner.
+ * Replaces the same reference lines (utils/train_test.py:18-64,128-132 + autograd), for the rows
+ *   users: out-tasks [user_task_begin,user_task_end) of g      items: [item_begin,item_end) (item ids),
+ *   whose in-tasks are [item_task_begin,item_task_end).
+ * Writes G[row] (local, rows owned) and zG[row] = dis[row] * G[row] into every rank's copy (`peers`, see above),
+ * neg_count[item_begin..item_end) (histogram of neg over the owned items), and ADDS sum_t softplus(..) of the owned
+ * users' triplets to accum[0].  out_trip / in_trip of g must hold GLOBAL triplet ids (lgcn_graph_remap_triplets when
+ * g was built from a shard of the edge list); num_triplets = the GLOBAL count P (loss normalisation);
+ * final_hat = the L2-NORMALISED final rows (lgcn_fwd_layer_ex with LGCN_FWD_NORMALIZED), complete on this rank for every
+ * row referenced; rnorm = 1/||final|| of the OWNED rows; trip_user / trip_pos complete for every triplet.
+ * G rows of owned nodes without tasks are never written: zero-initialise G once.
+ * ws.scalars != NULL (4*P floats; valid only when this call covers ALL users and items): per-triplet scalars are
+ * passed from the user pass to the item passes; NULL: they are recomputed from the rows (bit-identical). */
+typedef struct lgcn_bpr_owner_ws {
+    const int32_t *trip_user;   /* [P] user row of triplet t           (lgcn_triplet_index) */
+    const int32_t *trip_pos;    /* [P] positive item NODE id of triplet t                    */
+    int32_t *bucket_ptr;        /* [item_end - item_begin + 1]                                */
+    int32_t *bucket_cursor;     /* [item_end - item_begin]                                    */
+    int32_t *bucket;            /* [bucket_cap] triplet ids grouped by negative item          */
+    int64_t bucket_cap;         /* >= P                                                       */
+    float *scalars;             /* [4*P] or NULL                                              */
+    int32_t *sched;             /* [2] zero between launches                                  */
+} lgcn_bpr_owner_ws;
+
+int lgcn_bpr_owner(const lgcn_graph *g, const float *final_hat, const float *rnorm, const int64_t *neg,
+                   int64_t num_triplets, float *G, float *zG, int32_t *neg_count, double *accum,
+                   const lgcn_bpr_owner_ws *ws, int user_task_begin, int user_task_end, int item_task_begin,
+                   int item_task_end, int64_t item_begin, int64_t item_end, const lgcn_peers *peers, void *stream);
+
+/* trip_user[t] / trip_pos[t] for the triplets of the user rows covered by out-tasks [user_task_begin,user_task_end),
+ * stored into every rank's copy of the two tables (symmetric memory when peers != NULL).  One-off per edge list. */
+int lgcn_triplet_index(const lgcn_graph *g, int user_task_begin, int user_task_end, int32_t *trip_user,
+                       int32_t *trip_pos, const lgcn_peers *peers, void *stream);
+
+/* g was built from a SUBSET of an edge list (a rank's shard): rewrites its local triplet numbers
+ * (rank among the subset's user->movie edges) to the global ones, trip_global [g->num_triplets] int32 (device). */
+int lgcn_graph_remap_triplets(lgcn_graph *g, const int32_t *trip_global, void *stream);
+
 /* lgcn_clip_adam over rows [row_begin,row_end) only (accum must already hold the GLOBAL sums). */
 int lgcn_clip_adam_rows(const lgcn_adam *opt, float *user_w, float *item_w, int64_t num_users,
                         int64_t num_items, const float *grad, const double *accum,

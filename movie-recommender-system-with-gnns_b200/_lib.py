@@ -31,6 +31,7 @@ EXPORTS = [
     "lgcn_peer_barrier", "lgcn_score_topk_ex", "lgcn_graph_batched_sizes", "lgcn_graph_build_batched",
     "lgcn_train_steps_workspace_bytes", "lgcn_train_steps_sparse", "lgcn_probe_gather",
     "lgcn_score_topk_workspace_bytes", "lgcn_upload_lists",
+    "lgcn_bpr_owner", "lgcn_fwd_layer_ex", "lgcn_triplet_index", "lgcn_graph_remap_triplets", "lgcn_peer_allreduce4",
 ]
 
 
@@ -74,6 +75,11 @@ class CAdam(Structure):
 
 class CPeers(Structure):
     _fields_ = [("world", c_int32), ("rank", c_int32), ("mc_base", c_void_p), ("base", c_void_p * 8)]
+
+
+class CBprOwnerWs(Structure):
+    _fields_ = [("trip_user", c_void_p), ("trip_pos", c_void_p), ("bucket_ptr", c_void_p), ("bucket_cursor", c_void_p),
+                ("bucket", c_void_p), ("bucket_cap", c_int64), ("scalars", c_void_p), ("sched", c_void_p)]
 
 
 class CStepBuffers(Structure):
@@ -129,6 +135,8 @@ def lib():
     L.lgcn_prescale.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(CPeers), c_void_p]
     L.lgcn_fwd_layer.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 7 + \
         [c_int, c_int, c_int64, c_int64, POINTER(CPeers), c_void_p]
+    L.lgcn_fwd_layer_ex.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 7 + \
+        [c_int, c_int, c_int64, c_int64, c_int, POINTER(CPeers), c_void_p]
     L.lgcn_bwd_layer.argtypes = [POINTER(CGraph), c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, POINTER(CPeers),
                                  c_void_p]
@@ -136,6 +144,12 @@ def lib():
     L.lgcn_clip_adam_rows.argtypes = [POINTER(CAdam), c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                       c_float, c_void_p, c_int64, c_int64, c_void_p]
     L.lgcn_peer_barrier.argtypes = [POINTER(CPeers), c_void_p, c_void_p, c_void_p]
+    L.lgcn_peer_allreduce4.argtypes = [POINTER(CPeers), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.lgcn_bpr_owner.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, POINTER(CBprOwnerWs), c_int, c_int, c_int, c_int, c_int64, c_int64,
+                                 POINTER(CPeers), c_void_p]
+    L.lgcn_triplet_index.argtypes = [POINTER(CGraph), c_int, c_int, c_void_p, c_void_p, POINTER(CPeers), c_void_p]
+    L.lgcn_graph_remap_triplets.argtypes = [POINTER(CGraph), c_void_p, c_void_p]
     L.lgcn_train_step_sparse.argtypes = L.lgcn_train_step.argtypes
     L.lgcn_adam_flush.argtypes = [POINTER(CAdam), c_void_p, c_void_p, c_int64, c_int64, c_void_p]
     L.lgcn_graph_batched_sizes.argtypes = [c_int64, c_int64, c_void_p, POINTER(CBatchedSizes)]

@@ -26,7 +26,7 @@ int loss_finalize_impl(const double *, int64_t, float, float *, cudaStream_t);
 }  // namespace lgcn
 
 extern "C" const char *lgcn_last_error(void) { return lgcn::g_err; }
-extern "C" int lgcn_version(void) { return 100; }
+extern "C" int lgcn_version(void) { return 200; }
 
 static int check_buffers(const lgcn_step_buffers *b, bool grad) {
     LGCN_REQUIRE(b && b->final_emb && b->rnorm && b->neg_count && b->accum, LGCN_E_INVALID,

@@ -117,6 +117,7 @@ struct Range {
 };
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void f4add(float4 &a, const float4 &b) {
     a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;

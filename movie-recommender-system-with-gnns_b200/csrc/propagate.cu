@@ -97,6 +97,7 @@ struct FwdOp {
     float *final_out;
     float *rnorm;
     Peers peers;             // where produced rows go (all ranks' copies in the sharded path)
+    int norm_out;            // kLast: final_out receives final / ||final|| (every copy), rnorm 1/||final|| (LOCAL only)
 
     __device__ __forceinline__ void accumulate(int, int begin, int end, int lane, float4 &acc, float &, float &, float &) const {
         if constexpr (kFirst) GatherScaled<true>{nbr, dis, e0, nullptr}.run(begin, end, lane, acc);
@@ -119,10 +120,16 @@ struct FwdOp {
             f4fma(f, sq, s);
             f4fma(f, d, raw);
             f = f4scale(c0, f);
-            if (lane < 16) push4(reinterpret_cast<float4 *>(final_out) + (size_t)row * D4 + l16, f, peers);
-            if (rnorm) {
-                const float n2 = half_sum(f4dot(f, f));
-                if (lane == 0) push1(rnorm + row, 1.0f / sqrtf(n2), peers);
+            if (norm_out) {
+                const float rn = 1.0f / sqrtf(half_sum(f4dot(f, f)));
+                if (lane < 16) push4(reinterpret_cast<float4 *>(final_out) + (size_t)row * D4 + l16, f4scale(rn, f), peers);
+                if (lane == 0) rnorm[row] = rn;
+            } else {
+                if (lane < 16) push4(reinterpret_cast<float4 *>(final_out) + (size_t)row * D4 + l16, f, peers);
+                if (rnorm) {
+                    const float n2 = half_sum(f4dot(f, f));
+                    if (lane == 0) push1(rnorm + row, 1.0f / sqrtf(n2), peers);
+                }
             }
         }
     }
@@ -131,18 +138,19 @@ struct FwdOp {
 // Rows without any incident edge: final = e0 / (K+1)^2 (every propagated layer is zero).
 __global__ void __launch_bounds__(CTA_THREADS)
 fwd_inactive_kernel(Table e0, const uint8_t *__restrict__ active, int row0, int n, float c0,
-                    float *__restrict__ final_out, float *__restrict__ rnorm, Peers peers) {
+                    float *__restrict__ final_out, float *__restrict__ rnorm, Peers peers, int norm_out) {
     const int lane = threadIdx.x & 31, l16 = lane & 15;
     int row = row0 + (blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) * 2 + (lane >> 4);
     const bool ok = row < n && !active[row];
     float4 f = f4zero();
+    if (ok) f = f4scale(c0, ldg4(e0.row4(row) + l16));
+    const float rn = 1.0f / sqrtf(half_sum(f4dot(f, f)));
     if (ok) {
-        f = f4scale(c0, ldg4(e0.row4(row) + l16));
-        push4(reinterpret_cast<float4 *>(final_out) + (size_t)row * D4 + l16, f, peers);
-    }
-    if (rnorm) {
-        const float n2 = half_sum(f4dot(f, f));
-        if (ok && l16 == 0) push1(rnorm + row, 1.0f / sqrtf(n2), peers);
+        push4(reinterpret_cast<float4 *>(final_out) + (size_t)row * D4 + l16, norm_out ? f4scale(rn, f) : f, peers);
+        if (l16 == 0 && rnorm) {
+            if (norm_out) rnorm[row] = rn;
+            else push1(rnorm + row, rn, peers);
+        }
     }
 }
 
@@ -251,36 +259,44 @@ prescale_kernel(Table e0, const float *__restrict__ dis, int row0, int n, float 
 // per edge (single-GPU path); otherwise yin is the pre-scaled table y_{k-1} for every layer.
 int fwd_layer_impl(const lgcn_graph *g, const Table &e0, int k, int K, bool scaled_first, const float *yin,
                    float *yout, const float *y1, const float *y2, const float *y3, float *final_out,
-                   float *rnorm, Range r, cudaStream_t st, const Peers &peers) {
+                   float *rnorm, Range r, cudaStream_t st, const Peers &peers, int norm_out) {
     const float c0 = 1.0f / (float)((K + 1) * (K + 1));
     const bool first = k == 1 && scaled_first, last = k == K;
     if (last && r.inactive_rows && g->num_active < g->num_nodes && r.re > r.rb) {
         fwd_inactive_kernel<<<cdiv(r.re - r.rb, 2 * WARPS_PER_CTA), CTA_THREADS, 0, st>>>(
-            e0, g->active, r.rb, r.re, c0, final_out, rnorm, peers);
+            e0, g->active, r.rb, r.re, c0, final_out, rnorm, peers, norm_out);
         LGCN_LAUNCH_CHECK();
     }
     auto go = [&](auto op) { return launch_rowtasks(op, g->in_tasks, r.tb, r.te, g->partials, g->slot_counters, g->sched, st); };
     if (first && last)
         LGCN_CUDA(go(FwdOp<true, true>{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, nullptr, nullptr,
-                                       {nullptr, nullptr, nullptr}, 0, c0, final_out, rnorm, peers}));
+                                       {nullptr, nullptr, nullptr}, 0, c0, final_out, rnorm, peers, norm_out}));
     else if (first)
         LGCN_CUDA(go(FwdOp<true, false>{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, nullptr, yout,
-                                        {nullptr, nullptr, nullptr}, 0, c0, nullptr, nullptr, peers}));
+                                        {nullptr, nullptr, nullptr}, 0, c0, nullptr, nullptr, peers, 0}));
     else if (!last)
         LGCN_CUDA(go(FwdOp<false, false>{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, yin, yout,
-                                         {nullptr, nullptr, nullptr}, 0, c0, nullptr, nullptr, peers}));
+                                         {nullptr, nullptr, nullptr}, 0, c0, nullptr, nullptr, peers, 0}));
     else
         LGCN_CUDA(go(FwdOp<false, true>{nullptr, nullptr, g->in_ptr, g->in_nbr, g->dis, e0, yin, nullptr,
-                                        {y1, y2, y3}, K - 1, c0, final_out, rnorm, peers}));
+                                        {y1, y2, y3}, K - 1, c0, final_out, rnorm, peers, norm_out}));
     return LGCN_OK;
 }
 
-// One backward (Horner) layer j of K over the tasks of `r`; layer 1 gathers dis (.) G itself.
+int fwd_layer_impl(const lgcn_graph *g, const Table &e0, int k, int K, bool scaled_first, const float *yin,
+                   float *yout, const float *y1, const float *y2, const float *y3, float *final_out,
+                   float *rnorm, Range r, cudaStream_t st, const Peers &peers) {
+    return fwd_layer_impl(g, e0, k, K, scaled_first, yin, yout, y1, y2, y3, final_out, rnorm, r, st, peers, 0);
+}
+
+// One backward (Horner) layer j of K over the tasks of `r`; layer 1 gathers dis (.) G itself unless the caller
+// hands it the pre-scaled table z_0 = dis (.) G as `zin` (sharded path: the BPR epilogues store z_0 into
+// every rank's copy, G itself stays local).
 int bwd_layer_impl(const lgcn_graph *g, const float *G, int j, int K, const float *zin, float *zout,
                    const Table &e0, const int32_t *neg_count, float reg_coef, float *grad, double *accum,
                    Range r, cudaStream_t st, const Peers &peers) {
     const float c0 = 1.0f / (float)((K + 1) * (K + 1));
-    const bool first = j == 1, last = j == K;
+    const bool first = j == 1 && zin == nullptr, last = j == K;
     double *ex0 = accum ? accum + 1 : nullptr, *ex1 = accum ? accum + 2 : nullptr;
     if (last && r.inactive_rows && g->num_active < g->num_nodes && r.re > r.rb) {
         bwd_inactive_kernel<<<cdiv(r.re - r.rb, 2 * WARPS_PER_CTA), CTA_THREADS, 0, st>>>(
@@ -377,19 +393,29 @@ extern "C" int lgcn_prescale(const lgcn_graph *g, const float *user_w, const flo
     return LGCN_OK;
 }
 
-extern "C" int lgcn_fwd_layer(const lgcn_graph *g, const float *user_w, const float *item_w, int k, int num_layers,
-                              const float *yin, float *yout, const float *y1, const float *y2, const float *y3,
-                              float *final_out, float *rnorm, int task_begin, int task_end, int64_t row_begin,
-                              int64_t row_end, const lgcn_peers *peers, void *stream) {
+extern "C" int lgcn_fwd_layer_ex(const lgcn_graph *g, const float *user_w, const float *item_w, int k, int num_layers,
+                                 const float *yin, float *yout, const float *y1, const float *y2, const float *y3,
+                                 float *final_out, float *rnorm, int task_begin, int task_end, int64_t row_begin,
+                                 int64_t row_end, int flags, const lgcn_peers *peers, void *stream) {
     using namespace lgcn;
     LGCN_REQUIRE(g && user_w && item_w && yin && k >= 1 && k <= num_layers && num_layers <= 4, LGCN_E_INVALID,
                  "fwd_layer: bad argument");
     LGCN_REQUIRE(k == num_layers ? final_out != nullptr : yout != nullptr, LGCN_E_INVALID, "fwd_layer: missing output");
     LGCN_REQUIRE(task_begin >= 0 && task_end <= g->n_in_tasks && task_begin <= task_end, LGCN_E_INVALID,
                  "fwd_layer: task range [%d,%d) outside [0,%d)", task_begin, task_end, g->n_in_tasks);
+    const int norm_out = (flags & LGCN_FWD_NORMALIZED) ? 1 : 0;
+    LGCN_REQUIRE(!norm_out || k < num_layers || rnorm, LGCN_E_INVALID, "fwd_layer: LGCN_FWD_NORMALIZED needs rnorm");
     return fwd_layer_impl(g, Table{user_w, item_w, g->num_users}, k, num_layers, false, yin, yout, y1, y2, y3, final_out,
                           rnorm, Range{task_begin, task_end, (int)row_begin, (int)row_end, true}, (cudaStream_t)stream,
-                          make_peers(peers));
+                          make_peers(peers), norm_out);
+}
+
+extern "C" int lgcn_fwd_layer(const lgcn_graph *g, const float *user_w, const float *item_w, int k, int num_layers,
+                              const float *yin, float *yout, const float *y1, const float *y2, const float *y3,
+                              float *final_out, float *rnorm, int task_begin, int task_end, int64_t row_begin,
+                              int64_t row_end, const lgcn_peers *peers, void *stream) {
+    return lgcn_fwd_layer_ex(g, user_w, item_w, k, num_layers, yin, yout, y1, y2, y3, final_out, rnorm, task_begin,
+                             task_end, row_begin, row_end, 0, peers, stream);
 }
 
 extern "C" int lgcn_bwd_layer(const lgcn_graph *g, const float *grad_final, int j, int num_layers, const float *zin,
@@ -398,7 +424,7 @@ extern "C" int lgcn_bwd_layer(const lgcn_graph *g, const float *grad_final, int 
                               int64_t row_begin, int64_t row_end, const lgcn_peers *peers, void *stream) {
     using namespace lgcn;
     LGCN_REQUIRE(g && grad_final && j >= 1 && j <= num_layers && num_layers <= 4, LGCN_E_INVALID, "bwd_layer: bad argument");
-    LGCN_REQUIRE(j == 1 || zin, LGCN_E_INVALID, "bwd_layer: zin missing");
+    LGCN_REQUIRE(j == 1 || zin, LGCN_E_INVALID, "bwd_layer: zin missing");   // j == 1: zin = dis (.) G (optional)
     LGCN_REQUIRE(j == num_layers ? grad_e0 != nullptr : zout != nullptr, LGCN_E_INVALID, "bwd_layer: missing output");
     LGCN_REQUIRE(task_begin >= 0 && task_end <= g->n_out_tasks && task_begin <= task_end, LGCN_E_INVALID,
                  "bwd_layer: task range outside the list");

@@ -113,7 +113,62 @@ __global__ void peer_barrier_kernel(int *flags_local, int *epoch, Peers P, int r
     __threadfence_system();
 }
 
+// The step's three global sums (softplus sum, regulariser sum, ||grad||^2; accum[0..3], doubles) across ranks, riding
+// on the same flag protocol as the barrier: every rank stores its four doubles into slot [rank] of every rank's slot
+// table (symmetric memory), publishes its epoch, waits for all, then sums the slots IN RANK ORDER (every rank gets the
+// bit-identical total).  Replaces an NCCL all-reduce of 32 bytes; also a full barrier.
+__global__ void peer_allreduce4_kernel(int *flags_local, int *epoch, Peers P, int rank, double *slots_local,
+                                       double *accum) {
+    __shared__ int e_sh;
+    if ((int)threadIdx.x < P.world * 4) {
+        const int peer = threadIdx.x >> 2, j = threadIdx.x & 3;
+        double *dst = reinterpret_cast<double *>(reinterpret_cast<char *>(slots_local + rank * 4 + j) + P.delta[peer]);
+        const double v = accum[j];
+        asm volatile("st.relaxed.sys.global.f64 [%0], %1;" :: "l"(dst), "d"(v) : "memory");
+        __threadfence_system();
+    }
+    if (threadIdx.x == 0) {
+        const int e = epoch[0] + 1;
+        epoch[0] = e;
+        e_sh = e;
+        __threadfence_system();
+    }
+    __syncthreads();
+    const int e = e_sh;
+    if ((int)threadIdx.x < P.world) {
+        int *dst = reinterpret_cast<int *>(reinterpret_cast<char *>(flags_local + rank) + P.delta[threadIdx.x]);
+        asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(dst), "r"(e) : "memory");
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags_local + threadIdx.x) : "memory");
+        } while (v < e);
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (threadIdx.x < 4) {
+        double s = 0.0;
+        for (int r = 0; r < P.world; ++r) {
+            double v;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(slots_local + r * 4 + threadIdx.x) : "memory");
+            s += v;
+        }
+        accum[threadIdx.x] = s;
+    }
+}
+
 }  // namespace lgcn
+
+extern "C" int lgcn_peer_allreduce4(const lgcn_peers *peers, int32_t *flags_local, int32_t *epoch, double *slots_local,
+                                    double *accum, void *stream) {
+    using namespace lgcn;
+    LGCN_REQUIRE(peers && flags_local && epoch && slots_local && accum && peers->world >= 1 && peers->world <= 8,
+                 LGCN_E_INVALID, "peer_allreduce4: bad argument");
+    if (peers->world == 1) return LGCN_OK;
+    peer_allreduce4_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags_local, epoch, make_peers(peers), peers->rank,
+                                                              slots_local, accum);
+    LGCN_LAUNCH_CHECK();
+    return LGCN_OK;
+}
 
 extern "C" int lgcn_peer_barrier(const lgcn_peers *peers, int32_t *flags_local, int32_t *epoch, void *stream) {
     using namespace lgcn;

@@ -1,22 +1,26 @@
 """Node-range sharded full-graph LightGCN training step (BASELINE configs C3 / C5).
 
-One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  Every rank holds the full
-CSR pair of the edge list and executes only the warp tasks of the rows it OWNS: a contiguous user
-range plus a contiguous item range, each balanced by edge count, so that every rank gets its share
-of SpMM rows of both kinds and of BPR triplets (triplets follow their user).  Rows are
-owner-computed (no float atomics across ranks); the exchange steps are
+One process per GPU (``torch.distributed``; NVLink/NVSwitch peer memory for the data path).  Rank r OWNS a
+contiguous user range plus a contiguous item range, each balanced by work, and holds only its SHARD of the edge
+list: the edges with an owned endpoint (every edge has one user and one item endpoint, so it lives on at most two
+ranks).  From the shard it builds its own CSR pair (K0); the rows it owns are complete in it, the others are never
+executed.  Everything is owner-computed -- no float atomics, no reduction of a gradient table across ranks:
 
-    forward   all-gather of the owned slabs of y_k = dis (.) x_k before layer k+1     (K all-gathers)
-              all-gather of the final embeddings + their inverse norms (BPR reads remote rows)
-    BPR       all-reduce(sum) of dL/dfinal [N,64] and of the negative-sample histogram
-    backward  all-gather of z_j = dis (.) h_j before layer j+1                       (K-1 all-gathers)
-    clip      all-reduce of (softplus sum, regulariser sum, ||grad||^2)              (3 doubles)
+    forward   y_k = dis (.) x_k rows are stored into EVERY rank's copy from the SpMM epilogue (fused all-gather:
+              one NVLS multicast store, or `world` peer stores), a peer barrier separates layers   (K+1 barriers)
+    BPR       the user owner walks its users' triplets (loss, dL/dfinal[user]); the item owner walks the item's
+              in-edges (positive role) and the bucket of this step's negatives that hit the item (negative role);
+              per-triplet scalars are recomputed from the rows on both sides, so only embedding rows are ever read
+              remotely.  Epilogues store z_0 = dis (.) dL/dfinal into every copy               (1 barrier)
+    backward  K transpose-SpMM layers (Horner), z_j stored into every copy                     (K-1 barriers)
+    clip      the three global sums ride on a barrier (lgcn_peer_allreduce4)                    (1 barrier)
+    Adam      owned rows only -- no parameter all-reduce; ``gather_weights`` assembles full tables (checkpoints).
 
-Weights and Adam state are updated for owned rows only -- no parameter all-reduce; ``gather_weights``
-assembles the full tables (checkpointing).  With world_size 1 the result equals ``lgcn_train_step``.
+With world_size 1 the same code runs without exchange (and passes the triplet scalars instead of recomputing them).
+When symmetric memory cannot be set up the tables are exchanged by NCCL all-gathers between kernels instead.
 
-The orchestration is backend-agnostic (``ops``): ``CudaOps`` drives the C ABI; the CPU test-suite
-injects a torch stand-in to check the sharded algorithm over gloo with world_size 2.
+The orchestration is backend-agnostic (``ops``): ``CudaOps`` drives the C ABI; the CPU test-suite injects a torch
+stand-in to check the sharded algorithm over gloo with world_size 2.
 """
 from __future__ import annotations
 
@@ -69,15 +73,46 @@ class ShardPlan:
 
     @staticmethod
     def build(in_deg: torch.Tensor, out_deg: torch.Tensor, num_users: int, world: int, row_cost: int = 8) -> "ShardPlan":
-        w = (in_deg + out_deg + row_cost).cpu()
-        n = w.numel()
+        """Cost of a row = the rows its owner gathers for it per step: 2K SpMM gathers per incident edge, BPR gathers
+        per triplet role (a user plays one role per out-edge, an item one per in-edge plus, on average, P/I sampled
+        negatives), plus a constant per row."""
+        ind, outd = in_deg.cpu().double(), out_deg.cpu().double()
+        n = ind.numel()
+        num_items = n - num_users
+        w = ind + outd + row_cost
+        p = float(outd[:num_users].sum())
+        wi = w[num_users:] + (p / num_items if num_items else 0.0)
         up = balanced_boundaries(w[:num_users], world)
-        ip = [num_users + c for c in balanced_boundaries(w[num_users:], world)]
-        return ShardPlan(num_users, n - num_users, up, ip)
+        ip = [num_users + c for c in balanced_boundaries(wi, world)]
+        return ShardPlan(num_users, num_items, up, ip)
+
+
+@dataclass
+class EdgeShard:
+    """The part of an edge list a rank needs: edges with an owned endpoint, in their original relative order, plus the
+    GLOBAL triplet number (rank among ALL user->movie edges, utils/helpers.py:98-99) of its user->movie edges."""
+    edges: torch.Tensor            # [2, E_r] int64, global node ids
+    trip_global: Optional[torch.Tensor]   # [P_r] int32, None = identity (whole list)
+    num_triplets: int              # global P
+    num_edges: int                 # global E
+
+    @staticmethod
+    def build(edge_index: torch.Tensor, plan: ShardPlan, rank: int) -> "EdgeShard":
+        row, col = edge_index[0], edge_index[1]
+        is_trip = row < plan.num_users
+        p = int(is_trip.sum())
+        if plan.world == 1:
+            return EdgeShard(edge_index, None, p, edge_index.shape[1])
+        (ub, ue), (ib, ie) = plan.segments(rank)
+        own_r = ((row >= ub) & (row < ue)) | ((row >= ib) & (row < ie))
+        own_c = ((col >= ub) & (col < ue)) | ((col >= ib) & (col < ie))
+        keep = own_r | own_c
+        gt = torch.cumsum(is_trip.to(torch.int32), 0, dtype=torch.int32) - 1
+        return EdgeShard(edge_index[:, keep].contiguous(), gt[keep & is_trip].contiguous(), p, edge_index.shape[1])
 
 
 # ----------------------------------------------------------------------------------------------
-# collectives (plumbing)
+# collectives (plumbing; the CUDA data path exchanges through peer memory instead)
 # ----------------------------------------------------------------------------------------------
 
 class Comm:
@@ -120,38 +155,65 @@ class Comm:
 # ----------------------------------------------------------------------------------------------
 
 class CudaOps:
-    """The product backend: each method is one C-ABI call on the rank's row / task ranges.
+    """The product backend: each method is one C-ABI call over the rows this rank owns.
 
-    p2p=True (default when world > 1): the exchanged tables (y_k, z_j, final, rnorm) live in one
-    symmetric-memory region and the kernels store every produced row straight into all ranks' copies
-    (NVLS multicast store, or per-peer stores over NVLink) -- the all-gather is fused into the SpMM
-    epilogue and only a cross-rank barrier separates layers.  p2p=False: NCCL all-gathers between
-    kernels (also the fallback when symmetric memory cannot be set up)."""
+    ``edge_index``: the FULL [2,E] int64 edge list (CPU or CUDA tensor; the same on every rank) -- ``bind`` keeps only
+    this rank's shard on the device.  p2p (default when world > 1): the exchanged tables live in one symmetric-memory
+    region and the kernels store every produced row straight into all ranks' copies; p2p=False: NCCL all-gathers
+    between kernels (also the fallback when symmetric memory cannot be set up)."""
 
     def __init__(self, edge_index: torch.Tensor, num_users: int, num_items: int, num_layers: int,
                  lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0,
-                 p2p: Optional[bool] = None, group=None):
+                 p2p: Optional[bool] = None, group=None, device: Optional[torch.device] = None):
         from . import _lib
         self._lib = _lib
         self.L = _lib.lib()
-        self.dev = edge_index.device
-        self.g = _lib.Graph(edge_index, num_users, num_items)
+        self.dev = torch.device(device) if device is not None else (
+            edge_index.device if edge_index.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+        self.edge_index = edge_index
+        self.group = group
         self.nu, self.ni, self.n, self.k = num_users, num_items, num_users + num_items, num_layers
-        f32 = dict(dtype=torch.float32, device=self.dev)
-        n = self.n
-        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        if p2p is None:
-            p2p = world > 1 and os.environ.get("LGCN_P2P", "1") != "0"
-        nz = min(2, max(num_layers - 1, 0))
-        total = (num_layers + nz + 1) * n * DIM + n + 64          # + barrier flags (int32 view of the tail)
-        self.p2p, self.peers, self.hdl, self.p2p_error = False, None, None, None
+        self.hyper = (lr, betas, eps, max_norm)
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.want_p2p = (self.world > 1 and os.environ.get("LGCN_P2P", "1") != "0") if p2p is None else (p2p and self.world > 1)
+        self.p2p, self.peers, self.hdl, self.p2p_error, self.multicast = False, None, None, None, False
+        self.g = None
+
+    # -- graph facts the planner needs (global)
+    def degrees(self):
+        ei = self.edge_index
+        return torch.bincount(ei[1], minlength=self.n), torch.bincount(ei[0], minlength=self.n)
+
+    @property
+    def num_triplets(self) -> int:
+        return self.P
+
+    # -- setup ---------------------------------------------------------------------------------------
+    def bind(self, plan: ShardPlan, rank: int) -> None:
+        """Shard the edge list, build this rank's CSR pair, allocate the tables, index the triplets."""
+        self.plan, self.rank = plan, rank
+        self.segs = plan.segments(rank)
+        ei = self.edge_index
+        shard = EdgeShard.build(ei, plan, rank)
+        self.P, self.E = shard.num_triplets, shard.num_edges
+        self.shard = shard
+        self._alloc()
+        self.load_shard(shard.edges.to(self.dev), None if shard.trip_global is None else shard.trip_global.to(self.dev))
+
+    def _alloc(self) -> None:
+        lib_, n, k, dev = self._lib, self.n, self.k, self.dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        p = max(self.P, 1)
+        trip_words = 2 * p + (2 * p) % 2
+        # exchanged: y_0..y_{K-1}, z ping-pong (2), zg, final, rnorm, trip_user/trip_pos, accum slots, barrier flags
+        total = (k + 4) * n * DIM + (n + n % 2) + trip_words + 64 + 64
         flat = None
-        if p2p and world > 1:
+        if self.want_p2p:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                flat = symm_mem.empty(total, dtype=torch.float32, device=self.dev)
-                self.hdl = symm_mem.rendezvous(flat, group if group is not None else dist.group.WORLD)
-                c = _lib.CPeers()
+                flat = symm_mem.empty(total, dtype=torch.float32, device=dev)
+                self.hdl = symm_mem.rendezvous(flat, self.group if self.group is not None else dist.group.WORLD)
+                c = lib_.CPeers()
                 c.world, c.rank = self.hdl.world_size, self.hdl.rank
                 mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
                 if os.environ.get("LGCN_P2P_MULTICAST", "1") == "0":
@@ -167,76 +229,109 @@ class CudaOps:
         flat.zero_()
         off = 0
 
-        def take(rows_by_cols):
+        def take(count):
             nonlocal off
-            t = flat[off:off + rows_by_cols]
-            off += rows_by_cols
+            t = flat[off:off + count]
+            off += count
             return t
-        self.y = [take(n * DIM).view(n, DIM) for _ in range(num_layers)]          # y_0 .. y_{K-1}
-        self.z = [take(n * DIM).view(n, DIM) for _ in range(nz)]
+        self.y = [take(n * DIM).view(n, DIM) for _ in range(k)]                   # y_0 .. y_{K-1}
+        self.z = [take(n * DIM).view(n, DIM) for _ in range(2)]
+        self.zg = take(n * DIM).view(n, DIM)                                      # z_0 = dis (.) dL/dfinal
         self.final = take(n * DIM).view(n, DIM)
-        self.rnorm = take(n)
-        self.flags = take(64).view(torch.int32)                    # [0:8] = per-rank arrival epochs
-        self.epoch = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.rnorm = take(n + n % 2)[:n]
+        trip = take(trip_words).view(torch.int32)
+        self.trip_user, self.trip_pos = trip[:p], trip[p:2 * p]
+        self.slots = take(64).view(torch.float64)                                 # [8][4] doubles
+        self.flags = take(64).view(torch.int32)                                   # [0:8] = per-rank arrival epochs
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
         self._flat = flat
         if self.p2p:
-            torch.cuda.synchronize(self.dev)
-            self.hdl.barrier(channel=0)            # everyone has zeroed its region before the first flag lands
-            torch.cuda.synchronize(self.dev)
-        self.G = torch.zeros(n, DIM, **f32)
+            torch.cuda.synchronize(dev)
+            self.hdl.barrier(channel=0)            # everyone has zeroed its region before the first store lands
+            torch.cuda.synchronize(dev)
+        self.G = torch.zeros(n, DIM, **f32)        # dL/dfinal: owned rows only, never exchanged
         self.grad = torch.zeros(n, DIM, **f32)
-        self.neg_count = torch.zeros(num_items, dtype=torch.int32, device=self.dev)
-        self.scratch = torch.empty(2 * max(self.g.num_triplets, 1), **f32)
-        self.accum = torch.zeros(4, dtype=torch.float64, device=self.dev)
+        self.neg_count = torch.zeros(self.ni, dtype=torch.int32, device=dev)
+        self.accum = torch.zeros(4, dtype=torch.float64, device=dev)
         self.loss = torch.zeros(1, **f32)
         self.m, self.v = torch.zeros(n, DIM, **f32), torch.zeros(n, DIM, **f32)
-        self.step_count = torch.zeros(1, dtype=torch.int64, device=self.dev)
-        c = _lib.CAdam()
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        lr, betas, eps, max_norm = self.hyper
+        c = lib_.CAdam()
         c.lr, c.beta1, c.beta2, c.eps, c.max_norm = lr, betas[0], betas[1], eps, max_norm
         c.step, c.m, c.v = self.step_count.data_ptr(), self.m.data_ptr(), self.v.data_ptr()
         self.adam = c
-        self.in_rows = self.g.in_tasks.view(-1, 8)[: self.g.c.n_in_tasks, 0].cpu()
-        self.out_rows = self.g.out_tasks.view(-1, 8)[: self.g.c.n_out_tasks, 0].cpu()
-        self.local = None            # set by bind_segments(): rank-local task lists (one launch per layer)
+        # BPR workspace: buckets of the step's negatives over the owned items (+ scalars when nothing is sharded)
+        (_, _), (ib, ie) = self.segs
+        ni_own = ie - ib
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.bucket_ptr = torch.zeros(ni_own + 2, **i32)
+        self.bucket_cursor = torch.zeros(ni_own + 1, **i32)
+        self.bucket = torch.empty(p, **i32)
+        self.scalars = torch.empty(4 * p, **f32) if self.world == 1 else None
+        self.bpr_sched = torch.zeros(2, **i32)
+        w = lib_.CBprOwnerWs()
+        w.trip_user, w.trip_pos = self.trip_user.data_ptr(), self.trip_pos.data_ptr()
+        w.bucket_ptr, w.bucket_cursor = self.bucket_ptr.data_ptr(), self.bucket_cursor.data_ptr()
+        w.bucket, w.bucket_cap = self.bucket.data_ptr(), p
+        w.scalars = None if self.scalars is None else self.scalars.data_ptr()
+        w.sched = self.bpr_sched.data_ptr()
+        self.bpr_ws = w
 
-    def bind_segments(self, segs) -> None:
-        """Task order is free, so the tasks of ALL row segments this rank owns are packed into one
-        contiguous device list per direction: a layer is then ONE launch per rank (not one per
-        segment), and the ranges are resolved once instead of per call."""
-        import copy
+    def load_shard(self, edges_dev: torch.Tensor, trip_global_dev: Optional[torch.Tensor]) -> None:
+        """K0 on this rank's shard (already on the device) + global triplet numbers + the rank-local task lists + the
+        triplet index (exchanged).  Called by ``bind`` and again by callers that re-upload the edge list."""
         lib_ = self._lib
-        parts_in, parts_out, n_user_out = [], [], 0
-        for rb, re in segs:
-            tb, te = self._tasks(self.in_rows, rb, re)
-            parts_in.append(self.g.in_tasks.view(-1, 8)[tb:te])
-            tb, te = self._tasks(self.out_rows, rb, re)
-            parts_out.append(self.g.out_tasks.view(-1, 8)[tb:te])
-            if re <= self.nu:
-                n_user_out += te - tb
-        self.loc_in = torch.cat(parts_in).contiguous().view(-1)
-        self.loc_out = torch.cat(parts_out).contiguous().view(-1)
-        c = lib_.CGraph.from_buffer_copy(self.g.c)
-        c.in_tasks, c.out_tasks = self.loc_in.data_ptr(), self.loc_out.data_ptr()
-        c.n_in_tasks, c.n_out_tasks = self.loc_in.numel() // 8, self.loc_out.numel() // 8
-        c.n_out_user_tasks = n_user_out
+        g = lib_.Graph(edges_dev, self.nu, self.ni)
+        if trip_global_dev is not None:
+            if trip_global_dev.numel() != g.num_triplets:
+                raise lib_.LgcnError(f"shard has {g.num_triplets} user->movie edges, trip_global {trip_global_dev.numel()}")
+            lib_.check(self.L.lgcn_graph_remap_triplets(g.ref, trip_global_dev.data_ptr(), self._s()))
+        self.g = g
+        self._pack_tasks()
+        self.index_triplets()
+
+    def _pack_tasks(self) -> None:
+        """Task order is free (a split row's partials are reduced in slot order by whichever task arrives last), so
+        the tasks of both row segments this rank owns are packed into contiguous device lists, one launch per layer
+        and rank.  Every kernel pulls tasks from its list in order with a device counter: the lists are sorted by
+        DESCENDING edge count, so the last tasks a launch hands out are the cheapest ones and no warp is left alone
+        with a 512-edge task while the rest of the chip idles.  BPR walks user rows (out list) and item rows (in
+        list) separately: those two lists are kept apart, sorted the same way."""
+        g, lib_ = self.g, self._lib
+        in_t, out_t = g.in_tasks.view(-1, 8)[: g.c.n_in_tasks], g.out_tasks.view(-1, 8)[: g.c.n_out_tasks]
+        bounds = torch.tensor([b for seg in self.segs for b in seg], dtype=torch.int32, device=self.dev)
+        bi = torch.searchsorted(in_t[:, 0].contiguous(), bounds).tolist()
+        bo = torch.searchsorted(out_t[:, 0].contiguous(), bounds).tolist()
+
+        def by_size(t):
+            order = torch.sort(t[:, 2] - t[:, 1], descending=True, stable=True)[1]
+            return t[order]
+        in_u, in_i = in_t[bi[0]:bi[1]], in_t[bi[2]:bi[3]]
+        out_u, out_i = out_t[bo[0]:bo[1]], out_t[bo[2]:bo[3]]
+        self.loc_in = by_size(torch.cat([in_u, in_i])).contiguous().view(-1)          # SpMM forward: all owned rows
+        self.loc_out = by_size(torch.cat([out_u, out_i])).contiguous().view(-1)       # SpMM backward
+        self.bpr_users = by_size(out_u).contiguous().view(-1)                         # BPR user pass
+        self.bpr_items = by_size(in_i).contiguous().view(-1)                          # BPR item pass
         self.sched2 = torch.zeros(2, dtype=torch.int32, device=self.dev)
-        c.sched = self.sched2.data_ptr()
-        self.local = c
-        self.segs = list(segs)
-        self.all_active = self.g.num_active == self.n
 
-    # -- graph facts the planner needs
-    @property
-    def num_triplets(self) -> int:
-        return self.g.num_triplets
+        def view(in_list, out_list):
+            c = lib_.CGraph.from_buffer_copy(g.c)
+            c.in_tasks, c.out_tasks = in_list.data_ptr(), out_list.data_ptr()
+            c.n_in_tasks, c.n_out_tasks = in_list.numel() // 8, out_list.numel() // 8
+            c.n_in_user_tasks, c.n_out_user_tasks = 0, c.n_out_tasks
+            c.sched = self.sched2.data_ptr()
+            return c
+        self.local = view(self.loc_in, self.loc_out)
+        self.local_bpr = view(self.bpr_items, self.bpr_users)
+        # owned rows without any incident edge need the dense "inactive row" kernels
+        self.inactive_segs = [(rb, re) for rb, re in self.segs if re > rb and not bool(g.active[rb:re].all())]
 
-    def degrees(self):
-        return self.g.in_degree(), self.g.out_degree()
-
-    def _tasks(self, rows: torch.Tensor, rb: int, re: int) -> Tuple[int, int]:
-        b = int(torch.searchsorted(rows, torch.tensor(rb, dtype=rows.dtype)))
-        e = int(torch.searchsorted(rows, torch.tensor(re, dtype=rows.dtype)))
-        return b, e
+    def index_triplets(self) -> None:
+        if self.P == 0:
+            return
+        self._lib.check(self.L.lgcn_triplet_index(byref(self.local_bpr), 0, self.local_bpr.n_out_tasks,
+                                                  self.trip_user.data_ptr(), self.trip_pos.data_ptr(), self._p(), self._s()))
 
     def set_weights(self, user_w: torch.Tensor, item_w: torch.Tensor) -> None:
         self.uw, self.iw = user_w, item_w
@@ -247,75 +342,74 @@ class CudaOps:
     def _p(self):
         return byref(self.peers) if self.p2p else None
 
+    # -- exchange -----------------------------------------------------------------------------------
     def peer_barrier(self):
         """All ranks' rows of the table just produced have landed everywhere (stream-ordered)."""
         self._lib.check(self.L.lgcn_peer_barrier(byref(self.peers), self.flags.data_ptr(), self.epoch.data_ptr(),
                                                  self._s()))
 
+    def allreduce_accum(self):
+        self._lib.check(self.L.lgcn_peer_allreduce4(byref(self.peers), self.flags.data_ptr(), self.epoch.data_ptr(),
+                                                    self.slots.data_ptr(), self.accum.data_ptr(), self._s()))
+
+    # -- the step's stages ----------------------------------------------------------------------------
     def step_begin(self):
         self._lib.check(self.L.lgcn_step_begin(byref(self.adam), self.accum.data_ptr(), self._s()))
 
-    def prescale(self, rb, re):
-        self._lib.check(self.L.lgcn_prescale(self.g.ref, self.uw.data_ptr(), self.iw.data_ptr(), rb, re,
-                                             self.y[0].data_ptr(), self._p(), self._s()))
+    def prescale(self):
+        for rb, re in self.segs:
+            self._lib.check(self.L.lgcn_prescale(self.g.ref, self.uw.data_ptr(), self.iw.data_ptr(), rb, re,
+                                                 self.y[0].data_ptr(), self._p(), self._s()))
 
-    def fwd_layer(self, k, rb, re):
-        """Layer k over rows [rb,re); (rb,re) == (None,None): all of this rank's segments at once."""
-        if rb is None:
-            gref, tb, te, rb, re = byref(self.local), 0, self.local.n_in_tasks, 0, 0
-        else:
-            gref = self.g.ref
-            tb, te = self._tasks(self.in_rows, rb, re)
+    def _fwd_call(self, gref, k, tb, te, rb, re, normalized):
         last = k == self.k
         ys = [self.y[i].data_ptr() if i < self.k else None for i in (1, 2, 3)]
-        self._lib.check(self.L.lgcn_fwd_layer(
+        self._lib.check(self.L.lgcn_fwd_layer_ex(
             gref, self.uw.data_ptr(), self.iw.data_ptr(), k, self.k, self.y[k - 1].data_ptr(),
             None if last else self.y[k].data_ptr(), ys[0], ys[1], ys[2],
             self.final.data_ptr() if last else None, self.rnorm.data_ptr() if last else None, tb, te, rb, re,
-            self._p(), self._s()))
+            1 if (normalized and last) else 0, self._p(), self._s()))
 
-    def bpr(self, neg, urb, ure):
-        if self.local is not None:       # user tasks are the prefix of the packed by-source list; the item pass
-            gref, tb, te = byref(self.bpr_graph()), 0, self.local.n_out_user_tasks     # walks the GLOBAL by-target list
-        else:
-            gref = self.g.ref
-            tb, te = self._tasks(self.out_rows, urb, ure)
-        self._lib.check(self.L.lgcn_bpr_fwd_bwd_range(
-            gref, self.final.data_ptr(), self.rnorm.data_ptr(), neg.data_ptr(), self.G.data_ptr(),
-            self.neg_count.data_ptr(), self.scratch.data_ptr(), self.accum.data_ptr(), tb, te, urb, ure, self._s()))
+    def fwd_layer(self, k, normalized=True):
+        """normalized (training step): the last layer stores final / ||final|| into every copy of ``final`` and
+        1/||final|| of the owned rows into ``rnorm``; False (inference): the plain final embeddings."""
+        if k == self.k:
+            for rb, re in self.inactive_segs:                    # only the inactive-row kernel runs for an empty task range
+                self._fwd_call(self.g.ref, k, 0, 0, rb, re, normalized)
+        self._fwd_call(byref(self.local), k, 0, self.local.n_in_tasks, 0, 0, normalized)
 
-    def bpr_graph(self):
-        """Packed by-source tasks (pass A: own users) + the global by-target tasks (pass B: all items,
-        filtered by user range)."""
-        if getattr(self, "_bpr_c", None) is None:
-            c = self._lib.CGraph.from_buffer_copy(self.g.c)
-            c.out_tasks, c.n_out_tasks, c.n_out_user_tasks = self.local.out_tasks, self.local.n_out_tasks, self.local.n_out_user_tasks
-            c.sched = self.local.sched
-            self._bpr_c = c
-        return self._bpr_c
+    def bpr(self, neg):
+        (_, _), (ib, ie) = self.segs
+        c = self.local_bpr
+        self._lib.check(self.L.lgcn_bpr_owner(
+            byref(c), self.final.data_ptr(), self.rnorm.data_ptr(), neg.data_ptr(), self.P, self.G.data_ptr(),
+            self.zg.data_ptr(), self.neg_count.data_ptr(), self.accum.data_ptr(), byref(self.bpr_ws),
+            0, c.n_out_tasks, 0, c.n_in_tasks, ib - self.nu, ie - self.nu, self._p(), self._s()))
 
-    def bwd_layer(self, j, rb, re, bpr_coeff):
-        if rb is None:
-            gref, tb, te, rb, re = byref(self.local), 0, self.local.n_out_tasks, 0, 0
-        else:
-            gref = self.g.ref
-            tb, te = self._tasks(self.out_rows, rb, re)
+    def _bwd_call(self, gref, j, coeff, tb, te, rb, re):
         last = j == self.k
-        zin = None if j == 1 else self.z[j & 1].data_ptr()
+        zin = self.zg if j == 1 else self.z[j & 1]
         zout = None if last else self.z[(j - 1) & 1].data_ptr()
-        reg = 2.0 * bpr_coeff / (64.0 * self.g.num_triplets)
+        reg = 2.0 * coeff / (64.0 * self.P)
         self._lib.check(self.L.lgcn_bwd_layer(
-            gref, self.G.data_ptr(), j, self.k, zin, zout, self.uw.data_ptr(), self.iw.data_ptr(),
+            gref, self.G.data_ptr(), j, self.k, zin.data_ptr(), zout, self.uw.data_ptr(), self.iw.data_ptr(),
             self.neg_count.data_ptr(), reg, self.grad.data_ptr() if last else None, self.accum.data_ptr(),
             tb, te, rb, re, self._p(), self._s()))
+
+    def bwd_layer(self, j, bpr_coeff):
+        if j == self.k:
+            for rb, re in self.inactive_segs:
+                self._bwd_call(self.g.ref, j, bpr_coeff, 0, 0, rb, re)
+        self._bwd_call(byref(self.local), j, bpr_coeff, 0, self.local.n_out_tasks, 0, 0)
 
     def zbuf(self, j):
         return self.z[(j - 1) & 1]
 
-    def clip_adam(self, rb, re, bpr_coeff):
-        self._lib.check(self.L.lgcn_clip_adam_rows(
-            byref(self.adam), self.uw.data_ptr(), self.iw.data_ptr(), self.nu, self.ni, self.grad.data_ptr(),
-            self.accum.data_ptr(), self.g.num_triplets, bpr_coeff, self.loss.data_ptr(), rb, re, self._s()))
+    def clip_adam(self, bpr_coeff):
+        for rb, re in self.segs:
+            self._lib.check(self.L.lgcn_clip_adam_rows(
+                byref(self.adam), self.uw.data_ptr(), self.iw.data_ptr(), self.nu, self.ni, self.grad.data_ptr(),
+                self.accum.data_ptr(), self.P, bpr_coeff, self.loss.data_ptr(), rb, re, self._s()))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -332,16 +426,15 @@ class ShardedTrainer:
         self.bpr_coeff = bpr_coeff
         self.user_w, self.item_w = user_w, item_w
         ops.set_weights(user_w, item_w)
-        ind, outd = ops.degrees()
-        self.plan = plan if plan is not None else ShardPlan.build(ind, outd, ops.nu, self.comm.world)
-        self.segs = self.plan.segments(self.comm.rank)
+        if plan is None:
+            ind, outd = ops.degrees()
+            plan = ShardPlan.build(ind, outd, ops.nu, self.comm.world)
+        self.plan = plan
+        self.segs = plan.segments(self.comm.rank)
         self.k = ops.k
-        # one launch per layer when the backend can pack this rank's segments and no row is edge-less
-        self.packed = False
-        if hasattr(ops, "bind_segments"):
-            ops.bind_segments(self.segs)
-            self.packed = ops.all_active
-        self.layer_segs = [(None, None)] if self.packed else self.segs
+        ops.bind(plan, self.comm.rank)
+        if self.comm.world > 1 and not getattr(ops, "p2p", False):
+            self._gather_triplet_index()
 
     def _gather(self, buf: torch.Tensor, produced_by_kernel: bool = True) -> None:
         """Make every rank's copy of ``buf`` complete.  Tables produced by a p2p-enabled kernel are
@@ -352,49 +445,52 @@ class ShardedTrainer:
         self.comm.allgather_rows(buf, self.plan.user_ptr)
         self.comm.allgather_rows(buf, self.plan.item_ptr)
 
+    def _gather_triplet_index(self) -> None:
+        """Collective fallback: every triplet was indexed by exactly one rank (its user's owner), the other ranks hold
+        zeros there."""
+        o = self.ops
+        if o.num_triplets:
+            self.comm.allreduce(o.trip_user)
+            self.comm.allreduce(o.trip_pos)
+
     def step(self, neg: torch.Tensor) -> torch.Tensor:
-        """One step; ``neg`` is the FULL [P] negative vector (identical on every rank; each rank reads
-        the entries of its own triplets).  Returns the loss as a device tensor (same on every rank)."""
+        """One step; ``neg`` is the FULL [P] negative vector (identical on every rank).  Returns the loss as a device
+        tensor (same on every rank)."""
         o, k = self.ops, self.k
+        p2p = getattr(o, "p2p", False)
         o.step_begin()
-        for rb, re in self.segs:
-            o.prescale(rb, re)
+        o.prescale()
         self._gather(o.y[0])
         for layer in range(1, k + 1):
-            for rb, re in self.layer_segs:
-                o.fwd_layer(layer, rb, re)
+            o.fwd_layer(layer)
             if layer < k:
                 self._gather(o.y[layer])
-        self._gather(o.final)
-        if not getattr(o, "p2p", False):
-            self._gather(o.rnorm)             # (p2p: same kernel, same barrier as `final`)
-        urb, ure = self.segs[0]
-        o.bpr(neg, urb, ure)
-        self.comm.allreduce(o.G)
-        self.comm.allreduce(o.neg_count)
+        self._gather(o.final)                 # normalised rows; 1/||final|| stays with the owner
+        o.bpr(neg)
+        self._gather(o.zg)
         for j in range(1, k + 1):
-            for rb, re in self.layer_segs:
-                o.bwd_layer(j, rb, re, self.bpr_coeff)
+            o.bwd_layer(j, self.bpr_coeff)
             if j < k:
                 self._gather(o.zbuf(j))
-        self.comm.allreduce(o.accum)
-        for rb, re in self.segs:
-            o.clip_adam(rb, re, self.bpr_coeff)
+        if p2p:
+            o.allreduce_accum()
+        else:
+            self.comm.allreduce(o.accum)
+        o.clip_adam(self.bpr_coeff)
         return o.loss
 
     def step_sampled(self, num_items: Optional[int] = None, use_graph: bool = True) -> torch.Tensor:
         """One step with the reference's negative sampling (uniform ``randint`` per triplet,
         utils/helpers.py:79-80) done on the device.  All ranks must hold the same torch CUDA RNG state
         (same ``torch.manual_seed``) so that they draw identical negatives.  From the 4th call on the
-        whole step -- sampling, kernels, barriers, NCCL all-reduces -- is replayed as ONE CUDA graph
-        launch per rank, which removes the ~25 host calls per step that dominate at 8 GPUs."""
+        whole step -- sampling, kernels, peer barriers -- is replayed as ONE CUDA graph launch per rank."""
         ni = self.plan.num_items if num_items is None else num_items
         p, dev = self.ops.num_triplets, self.user_w.device
         self._calls = getattr(self, "_calls", 0) + 1
         if not use_graph or not self.user_w.is_cuda or getattr(self, "_graph_failed", False):
             return self.step(torch.randint(0, ni, (p,), device=dev))
         if getattr(self, "_graph", None) is None:
-            if self._calls <= 3:                       # eager warm-up (NCCL channels, allocator)
+            if self._calls <= 3:                       # eager warm-up (allocator, lazy module loading)
                 return self.step(torch.randint(0, ni, (p,), device=dev))
             try:
                 torch.cuda.synchronize(dev)
@@ -410,6 +506,11 @@ class ShardedTrainer:
         self._graph.replay()
         return self._graph_loss
 
+    def drop_graph(self) -> None:
+        """Forget the captured step (its launches hold the addresses of the current CSR arrays)."""
+        self._graph = None
+        self._calls = 0
+
     def gather_weights(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """Full, up-to-date tables on every rank (for state_dict / best_model.pth)."""
         nu = self.plan.num_users
@@ -420,12 +521,10 @@ class ShardedTrainer:
     def propagate_only(self) -> torch.Tensor:
         """Forward propagation alone (BASELINE config C3's per-layer timing): returns final [N,64]."""
         o, k = self.ops, self.k
-        for rb, re in self.segs:
-            o.prescale(rb, re)
+        o.prescale()
         self._gather(o.y[0])
         for layer in range(1, k + 1):
-            for rb, re in self.layer_segs:
-                o.fwd_layer(layer, rb, re)
+            o.fwd_layer(layer, normalized=False)
             if layer < k:
                 self._gather(o.y[layer])
         self._gather(o.final)

@@ -152,10 +152,18 @@ class FusedAdam:
     def zero_grad(self):
         pass
 
+    def zero_sparse_invariants(self):
+        """The touched-rows steps need dL/dfinal and the negative histogram all-zero on entry (they leave them
+        all-zero on exit); a dense step in between leaves both dirty."""
+        if self.dirty:
+            self.buffers.grad_final.zero_()
+            self.buffers.neg_count.zero_()
+            self.dirty = False
+
     def graph_ready(self, g, sparse: bool) -> bool:
         """Capturing freezes buffer addresses: the scratch must already fit this batch, the bias
         table must have room, and the zero-invariants of the sparse step must hold."""
-        return (self.buffers.trip_scratch.numel() >= 2 * g.num_triplets and not (sparse and self.dirty)
+        return (self.buffers.trip_scratch.numel() >= 2 * g.num_triplets
                 and self.host_steps + (1 << 12) < self.bc_table.shape[0])
 
     def state_dict(self):
@@ -169,6 +177,9 @@ class FusedAdam:
         self.host_steps = int(self.step_count)
         self.row_step.fill_(self.host_steps)
         self.pending = False
+        self.graphs.clear()               # captured launches hold the old bias table and the old hyper-parameters by value
+        self.captured = 0
+        self.dirty = True                 # whatever the scratch holds belongs to another timeline
         self.buffers.neg_flag.zero_()     # step stamps of another timeline
         self.buffers.act_stamp.zero_()
         self._bc_table(max(1 << 16, 2 * self.host_steps + 4))
@@ -180,6 +191,13 @@ class _Stage:
 
     def __init__(self):
         self.edges = self.arena = self.workspace = self.current = self.uploading = None
+
+
+def _check_neg(neg: torch.Tensor, num_items: int) -> None:
+    """Caller-supplied negatives index rows of the item table on the device: refuse ids outside [0, I) here (one
+    small reduction + read-back; negatives sampled by this module need no check)."""
+    if neg.numel() and bool(((neg < 0) | (neg >= num_items)).any()):
+        raise LgcnError(f"neg holds item ids outside [0, {num_items})")
 
 
 def train_step(model, optimizer: FusedAdam, edge_index: torch.Tensor, neg: Optional[torch.Tensor] = None,
@@ -196,7 +214,9 @@ def train_step(model, optimizer: FusedAdam, edge_index: torch.Tensor, neg: Optio
         raise LgcnError("batch has no user->movie edge: the reference's loss is NaN here (SURVEY App. B #13)")
     if neg is None:
         neg = torch.randint(0, model.num_items, (g.num_triplets,), device=dev)
-    require_cuda(neg, "neg", torch.int64)
+    else:
+        require_cuda(neg, "neg", torch.int64)
+        _check_neg(neg, model.num_items)
     if neg.numel() != g.num_triplets:
         raise LgcnError(f"neg has {neg.numel()} entries, the batch has {g.num_triplets} user->movie edges")
     if loss_out is None:
@@ -207,10 +227,7 @@ def train_step(model, optimizer: FusedAdam, edge_index: torch.Tensor, neg: Optio
     optimizer.buffers.ensure_triplets(g.num_triplets)
     optimizer._count_step()
     if sparse:
-        if optimizer.dirty:                # dense steps leave dL/dfinal / the histogram dirty
-            optimizer.buffers.grad_final.zero_()
-            optimizer.buffers.neg_count.zero_()
-            optimizer.dirty = False
+        optimizer.zero_sparse_invariants()
         optimizer.pending = True
     else:
         optimizer.flush()
@@ -276,10 +293,7 @@ def _launch_steps(model, opt, graphs, neg_all, loss_ptr, bpr_coeff, device, cg=N
     need = L.lgcn_train_steps_workspace_bytes(b)
     if buf.steps_ws.numel() < need:
         buf.steps_ws = torch.empty(2 * need, dtype=torch.uint8, device=device)
-    if opt.dirty:                      # dense steps leave dL/dfinal / the histogram dirty
-        buf.grad_final.zero_()
-        buf.neg_count.zero_()
-        opt.dirty = False
+    opt.zero_sparse_invariants()
     opt.pending = True
     opt._count_step(b)
     if cg is None:
@@ -302,6 +316,7 @@ def train_steps(model, optimizer: FusedAdam, edge_indices: Sequence[torch.Tensor
     dev = edge_indices[0].device
     neg_all = None if negs is None else torch.cat([n.reshape(-1) for n in negs])
     if negs is not None:
+        _check_neg(neg_all, model.num_items)
         for g, n in zip(graphs, negs):
             if n.numel() != g.num_triplets:
                 raise LgcnError(f"neg has {n.numel()} entries, the batch has {g.num_triplets} user->movie edges")
@@ -358,10 +373,7 @@ def _single_step(model, optimizer, g, num_edges, device, weights, slots, cap) ->
     optimizer.buffers.ensure_triplets(g.num_triplets)
     optimizer._count_step()
     if sparse:
-        if optimizer.dirty:
-            optimizer.buffers.grad_final.zero_()
-            optimizer.buffers.neg_count.zero_()
-            optimizer.dirty = False
+        optimizer.zero_sparse_invariants()
         optimizer.pending = True
     else:
         optimizer.flush()
@@ -433,6 +445,7 @@ def _train_epoch_fused(model, optimizer: "FusedAdam", train_loader, device) -> f
         if entry is not None and entry[1] is not None:                      # replay
             optimizer._count_step()
             if sparse:
+                optimizer.zero_sparse_invariants()      # a dense step in between leaves dL/dfinal / the histogram dirty
                 optimizer.pending = True
             else:
                 optimizer.flush()
@@ -446,6 +459,8 @@ def _train_epoch_fused(model, optimizer: "FusedAdam", train_loader, device) -> f
             optimizer._count_step()
             if not sparse:
                 optimizer.flush()
+            if sparse:
+                optimizer.zero_sparse_invariants()
             cg = torch.cuda.CUDAGraph()
             with torch.cuda.graph(cg):
                 neg = torch.randint(0, model.num_items, (g.num_triplets,), device=device)
@@ -512,6 +527,10 @@ def eval_loss(model, edge_index: torch.Tensor, neg: torch.Tensor, buffers: Optio
     dev = edge_index.device
     if buffers is None:
         buffers = StepBuffers(g.num_nodes, model.num_items, model.num_layers, dev)
+    require_cuda(neg, "neg", torch.int64)
+    _check_neg(neg, model.num_items)
+    if neg.numel() != g.num_triplets:
+        raise LgcnError(f"neg has {neg.numel()} entries, the edge list has {g.num_triplets} user->movie edges")
     out = torch.empty(1, dtype=torch.float32, device=dev)
     check(lib().lgcn_eval_loss(g.ref, model.user_embedding.weight.data_ptr(), model.item_embedding.weight.data_ptr(),
                                model.num_layers, neg.contiguous().data_ptr(), bpr_coeff, buffers.ref, out.data_ptr(),
@@ -548,7 +567,7 @@ def compute_recall_at_k(embs, k: int = 20, num_samples: int = 10, sample_size: i
         idx = sampled[s] if sampled is not None else np.random.choice(num_users, sample_size, replace=False)
         rows = user_embs[torch.as_tensor(idx, device=user_embs.device)].contiguous()
         top_idx, _ = score_topk(rows, cand, k, normalize=True)
-        hits = (top_idx < p).sum(dim=1).to(torch.float32)
+        hits = ((top_idx >= 0) & (top_idx < p)).sum(dim=1).to(torch.float32)   # -1 pads lists shorter than k
         total += (hits / p).mean().item()
     return total / num_samples
 

@@ -32,20 +32,22 @@ def test_header_and_library_agree(L):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.lgcn_version() == 100
+    assert L.lgcn_version() == 200
     assert isinstance(L.lgcn_last_error(), bytes)
 
 
 def test_struct_layouts_match_c(tmp_path, L):
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include "lgcn_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    prog.write_text('#include <stdio.h>\n#include "lgcn_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                     'sizeof(lgcn_task),sizeof(lgcn_graph),sizeof(lgcn_graph_sizes),sizeof(lgcn_adam),'
-                    'sizeof(lgcn_step_buffers),offsetof(lgcn_graph,partials));return 0;}\n')
+                    'sizeof(lgcn_step_buffers),offsetof(lgcn_graph,partials),sizeof(lgcn_bpr_owner_ws),'
+                    'sizeof(lgcn_peers),offsetof(lgcn_bpr_owner_ws,scalars));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), str(prog), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     got = [ctypes.sizeof(_lib.CTask), ctypes.sizeof(_lib.CGraph), ctypes.sizeof(_lib.CGraphSizes),
-           ctypes.sizeof(_lib.CAdam), ctypes.sizeof(_lib.CStepBuffers), _lib.CGraph.partials.offset]
+           ctypes.sizeof(_lib.CAdam), ctypes.sizeof(_lib.CStepBuffers), _lib.CGraph.partials.offset,
+           ctypes.sizeof(_lib.CBprOwnerWs), ctypes.sizeof(_lib.CPeers), _lib.CBprOwnerWs.scalars.offset]
     assert [int(x) for x in out] == got
 
 
