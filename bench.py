@@ -1,16 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- LightGCN hot-path benchmark (contract in the task statement / DESIGN.md sec. Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c5|c2|c4]
 
-N = 1  workload C2 (BASELINE.json configs[1]): Cluster-GCN training on the synthetic ML-25M-shaped
-       graph (162,541 users x 59,047 movies, 25.0 M directed edges, 90 % train, 100 METIS parts,
-       K = 3, dim 64).  One STEP = one training epoch = 100 cluster-batch iterations of
-       utils/train_test.py:86-101 (forward, BPR loss, backward, clip, Adam).
-N > 1  workload C3: full-graph training step on the same graph, node-range sharded (see
-       lgcn_b200/sharded.py); launched under torchrun, one rank per GPU.
-metric  lightgcn_train_edges_per_s = directed batch-graph edges consumed per second by full training
-        steps (whole job); ms_per_step is the epoch (N=1) / full-graph step (N>1) time.
+EVERY N runs the SAME workload, so the per-N lines are a like-for-like strong-scaling curve:
+
+  C3 (BASELINE.json configs[2], default)  one full-graph LightGCN training step -- forward (K = 3 propagation
+      layers), BPR loss, backward, clip, Adam (utils/train_test.py:88-96) -- on the synthetic ML-25M-shaped
+      graph (162,541 users x 59,047 movies, 25.0 M directed edges, 22.5 M of them train), node-range sharded
+      over the N GPUs (lgcn_b200/sharded.py).  A full-graph step IS a full-graph epoch.
+  C5 (--workload c5, configs[4])          the same step on the 10x graph (1.6 M x 0.6 M, 225 M train edges, K = 4).
+
+metric  lightgcn_train_edges_per_s = directed train edges consumed per second by full training steps
+        (whole job); ms_per_step is the step (= full-graph epoch) time, max over ranks.
+At N = 1 (C3) the line also carries, as named blocks with their own roofline / e2e / cpu_baseline:
+  cluster_gcn_epoch_c2   BASELINE configs[1]: one Cluster-GCN epoch (100 METIS parts) through train()
+  eval_full_rank_c4      BASELINE configs[3]: 162,541 x 59,047 scoring + train mask + top-20
+  spmm_full_graph        K-layer propagation alone (edges/s, GB/s against the HBM and the L2-gather ceilings)
 """
 from __future__ import annotations
 
@@ -33,6 +39,7 @@ from lgcn_b200.data import synthetic  # noqa: E402
 
 METRIC, UNIT = "lightgcn_train_edges_per_s", "edges/s"
 NUM_PARTS = 100
+SHAPE_OF = {"c3": "ml25m", "c5": "ml25m_x10", "c2": "ml25m", "c1": "ml100k", "c4": "ml25m"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -63,6 +70,29 @@ def cluster_batches_cpu(train: torch.Tensor, cluster: torch.Tensor, num_nodes: i
     off = torch.zeros(NUM_PARTS + 1, dtype=torch.long)
     off[1:] = torch.cumsum(cnt, 0)
     return [e[:, off[p]:off[p + 1]].contiguous() for p in range(NUM_PARTS)]
+
+
+def shared_train_edges(shape: str, local_rank: int, barrier):
+    """(num_users, num_items, train [2,E] int64 CPU tensor).  Under torchrun only local rank 0 generates the
+    synthetic graph (the 10x graph needs ~60 GB of host memory while it is being built); the others read it
+    from /dev/shm after a barrier."""
+    nu, ni = synthetic.SHAPES[shape][0], synthetic.SHAPES[shape][1]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        g = synthetic.make_graph(shape, seed=0)
+        return g.num_users, g.num_items, g.edges("train"), g
+    path = f"/dev/shm/lgcn_b200_{shape}_seed0_train_{os.environ.get('MASTER_PORT', '0')}.npy"
+    if local_rank == 0:
+        g = synthetic.make_graph(shape, seed=0)
+        np.save(path + ".tmp.npy", g.edges("train").numpy().astype(np.int32))
+        os.replace(path + ".tmp.npy", path)
+        del g
+    barrier()
+    tr = torch.from_numpy(np.load(path)).to(torch.int64)
+    barrier()
+    if local_rank == 0:
+        os.remove(path)
+    return nu, ni, tr, None
 
 
 class ClockSampler:
@@ -112,234 +142,6 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# --------------------------------------------------------------------------------------------
-# CPU arm: the oracle port timed on the host cores (also `--impl reference`)
-# --------------------------------------------------------------------------------------------
-
-def cpu_sample_batches(batches):
-    """Three cluster batches at the 25/50/75-th size percentile: the per-batch CPU cost is dominated
-    by full-table (N x 64) work, so the epoch estimate is 100 x their mean time."""
-    sizes = np.array([b.shape[1] for b in batches])
-    order = np.argsort(sizes)
-    return [int(order[int(q * (len(order) - 1))]) for q in (0.25, 0.5, 0.75)]
-
-
-def run_cpu_arm(g, batches, k, steps, warmup):
-    from oracle import reference_path as ref
-    torch.set_num_threads(os.cpu_count() or 1)
-    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
-    st = ref.TrainState(u0, i0, k)
-    pick = cpu_sample_batches(batches)
-    gen = torch.Generator().manual_seed(0)
-    total_edges = int(sum(b.shape[1] for b in batches))
-
-    def one_step():
-        t0 = time.perf_counter()
-        for p in pick:
-            ei = batches[p]
-            neg = torch.randint(0, g.num_items, (int((ei[0] < g.num_users).sum()),), generator=gen)
-            st.step(ei, neg)
-        return time.perf_counter() - t0
-
-    for _ in range(warmup):
-        one_step()
-    times = [one_step() for _ in range(steps)]
-    per_batch = float(np.mean(times)) / len(pick)
-    epoch_s = per_batch * len(batches)
-    sample = (f"{len(pick)} of {len(batches)} cluster batches per step (25/50/75th size percentile: "
-              f"{[int(batches[p].shape[1]) for p in pick]} edges), epoch time = {len(batches)} x mean batch time")
-    return {"value": total_edges / epoch_s, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": sample, "epoch_ms_estimate": epoch_s * 1e3, "ms_per_batch": per_batch * 1e3}
-
-
-# --------------------------------------------------------------------------------------------
-# ours, N = 1 (C2)
-# --------------------------------------------------------------------------------------------
-
-def run_c2(args):
-    from lgcn_b200 import _lib
-    from lgcn_b200.data.dataset_handler import ClusterData, ClusterLoader, Data
-    from lgcn_b200.models.light_gcn import LightGCN
-    from lgcn_b200.utils import train_test as tt
-
-    shape = {"c2": "ml25m", "c1": "ml100k"}[args.workload]
-    dev = torch.device("cuda:0")
-    torch.cuda.set_device(dev)
-    g = synthetic.make_graph(shape, seed=0)
-    k = synthetic.SHAPES[shape][3]
-    train = g.edges("train")
-    n = g.num_nodes
-    cluster = load_partition(train, n, shape)
-    t0 = time.perf_counter()
-    cd = ClusterData(Data(edge_index=train.to(dev), num_nodes=n), NUM_PARTS, cluster=cluster)
-    torch.cuda.synchronize()
-    extract_ms = (time.perf_counter() - t0) * 1e3
-    parts = [d for d in cd.parts]
-    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
-    model = LightGCN(g.num_users, g.num_items, num_layers=k).to(dev)
-    with torch.no_grad():
-        model.user_embedding.weight.copy_(u0)
-        model.item_embedding.weight.copy_(i0)
-    opt = tt.FusedAdam(model)
-    loader = ClusterLoader(parts, shuffle=True)
-    t0 = time.perf_counter()
-    graphs = [model.graph(d.edge_index) for d in parts]          # K0 once per batch tensor (cached)
-    torch.cuda.synchronize()
-    build_ms = (time.perf_counter() - t0) * 1e3
-    live = [d for d, gr in zip(parts, graphs) if gr.num_triplets > 0]
-    edges_per_epoch = int(sum(d.edge_index.shape[1] for d in live))
-    torch.manual_seed(0)
-
-    def epoch():
-        return tt.train(model, opt, loader, dev)
-
-    for _ in range(args.warmup):
-        epoch()
-    torch.cuda.synchronize()
-    clocks = ClockSampler(0)
-    clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record()
-    losses = [epoch() for _ in range(args.steps)]
-    ev1.record()
-    torch.cuda.synchronize()
-    total_ms = ev0.elapsed_time(ev1)
-    clk = clocks.stop()
-    ms_per_step = total_ms / args.steps
-    value = edges_per_epoch / (ms_per_step * 1e-3)
-
-    # ---- e2e: the same epoch through train() with HOST batches (pinned), H2D every step ----------
-    host_parts = [Data(edge_index=d.edge_index.cpu().pin_memory(), num_nodes=n) for d in live]
-
-    class HostLoader:
-        """What the reference's DataLoader hands to train(): batches that live on the HOST (pinned);
-        train() uploads them (utils/train_test.py:87 `batch.to(device)`) every epoch."""
-        def __iter__(self):
-            return iter(host_parts)
-
-    model._graphs.capacity = 4                                     # per-step uploads must not pile up
-    for _ in range(2):
-        tt.train(model, opt, HostLoader(), dev)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(1, args.steps)
-    e0.record()
-    for _ in range(e2e_steps):
-        tt.train(model, opt, HostLoader(), dev)                    # returns after the loss D2H
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1) / e2e_steps
-    model._graphs.capacity = 512
-    h2d = int(sum(hp.edge_index.numel() * 8 for hp in host_parts))
-    e2e = {"value": edges_per_epoch / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * len(host_parts) + 8 * (16 * len(host_parts) + 1),
-           "note": "train() over HOST (pinned) batches: every epoch uploads all edge lists, rebuilds every batch's "
-                   "normalisation/CSR (one batched K0b call) and reads the losses back"}
-
-    # ---- per-stage device times of the DENSE step over one epoch (events on the launch stream) ----
-    stage_ms = stage_breakdown(model, opt, live, graphs_of(model, live), k, dev)
-    peak, peak_src = measured_peak_gbs()
-    adam_bytes = 7 * n * 256                                       # p,m,v,grad read + p,m,v written
-    adam_ms = stage_ms["clip_adam"] / len(live)
-    spmm = full_graph_propagation(model, train.to(dev), k, dev, peak)
-    # roofline kernel = the propagation layer (SURVEY.md sec.8d defines B_layer for it): one launch = one
-    # layer over the train graph, duration = event time of the K-layer call / K
-    b_layer = 2 * n * 256 + 8 * train.shape[1] + 4 * (n + 1)
-    layer_ms = spmm["ms"] / k
-    roofline = {"kernel": "rowtask_kernel<FwdOp> (one propagation layer, full train graph)", "bound": "hbm",
-                "achieved": b_layer / (layer_ms * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "traffic": ncu_traffic("rowtask_fwd_layer"), "algorithmic_bytes_per_launch": b_layer,
-                "avg_launch_ms": layer_ms,
-                "note": "table (56.7 MB) is L2-resident, so the kernel is bound by the L2 gather rate, not by the compulsory "
-                        "HBM bytes: see l2_gather (gather-model bytes E*264 + N*256 per layer against the measured "
-                        "random-row-gather ceiling of the L2)"}
-    roofline["frac"] = roofline["achieved"] / peak
-    roofline["l2_gather"] = {"achieved": spmm["gather_model_gbs"], "peak": spmm["l2_gather_ceiling_gbs"], "unit": "GB/s",
-                             "frac": spmm["frac_of_l2_gather_ceiling"], "peak_source": spmm["l2_gather_ceiling_how"]}
-    roofline_adam = {"kernel": "clip_adam_kernel (dense step)", "bound": "hbm",
-                     "achieved": adam_bytes / (adam_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "traffic": ncu_traffic("clip_adam"), "algorithmic_bytes_per_launch": adam_bytes,
-                     "avg_launch_ms": adam_ms}
-    roofline_adam["frac"] = roofline_adam["achieved"] / peak
-    # the kernel the epoch actually spends its time in: one persistent launch per epoch (epoch_kernel.cu).
-    # Algorithmic bytes per step: Adam state of the touched rows (p, m, v read + written) + the activation rows
-    # of the active nodes (y0..y_{K-1}, final, G, z tables, grad: written once, read once or K times) + indices.
-    grs = graphs_of(model, live)
-    step_bytes = 0
-    for gr in grs:
-        touched = gr.num_active + min(gr.num_triplets, g.num_items)
-        step_bytes += touched * 256 * 6 + gr.num_active * 256 * (2 * (2 * k + 3)) + gr.num_edges * 4 * (2 * k + 4)
-    roofline_step = {"kernel": "epoch_kernel (lgcn_train_steps_sparse: all sparse steps of an epoch in one launch)",
-                     "bound": "hbm", "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "algorithmic_bytes_per_launch": step_bytes, "avg_launch_ms": ms_per_step,
-                     "traffic": ncu_traffic("epoch_kernel"),
-                     "note": "latency-bound by construction: ~2 k rows and ~7 k edges per step, 2K+2 device-wide barriers "
-                             "per step (see profiles/r1c_epoch_trace.txt for where a step goes); duration here is the whole "
-                             "epoch (kernel + end-of-epoch flush)"}
-    roofline_step["frac"] = roofline_step["achieved"] / peak
-    n_sparse = sum(1 for gr in grs if tt.sparse_step_pays(gr))
-    # per epoch: the sparse batches run inside ONE persistent cooperative launch (epoch_kernel) followed by one
-    # adam_replay_kernel (flush); a dense batch is launches_per_step(k, False) kernels
-    launches = args.steps * ((2 if n_sparse else 0) + (len(live) - n_sparse) * launches_per_step(k, False))
-
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"C2 Cluster-GCN training epoch, {shape} shape: U={g.num_users} I={g.num_items} "
-                                  f"E_train={train.shape[1]} directed, {NUM_PARTS} METIS parts "
-                                  f"({len(live)} non-empty, {edges_per_epoch} intra-cluster edges), K={k}, dim=64, "
-                                  "fwd+BPR+bwd+clip+Adam per batch, step = 1 epoch",
-                      "l2": "an epoch touches ~0.9 GB of distinct rows/state (100 batches x ~9 MB) plus 24 MB of CSR, "
-                            "more than the 126 MB L2; no explicit flush",
-                      "parallelism": "1 GPU",
-                      "step_kinds": f"{n_sparse} touched-rows (sparse) steps inside one persistent cooperative launch "
-                                    f"(lgcn_train_steps_sparse) + {len(live) - n_sparse} dense steps per epoch"},
-           "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-           "roofline": roofline, "roofline_adam": roofline_adam, "roofline_step_kernel": roofline_step,
-           "dense_stage_ms_per_epoch": stage_ms,
-           "spmm_full_graph": spmm,
-           "setup_ms": {"cluster_extract": extract_ms, "graph_build_100_batches": build_ms},
-           "final_epoch_loss": losses[-1]}
-    if args.workload == "c2" and not args.no_eval:
-        try:
-            out["full_graph_step_1gpu_c3"] = full_graph_step_single_gpu(g, k, dev)
-        except Exception as exc:                                    # an extra, never the reason for a missing line
-            out["full_graph_step_1gpu_c3"] = {"error": repr(exc)[:200]}
-    if not args.no_cpu:
-        out["cpu_baseline"] = run_cpu_arm(g, cluster_batches_cpu(train, cluster, n), k, 2, 1)
-    return out
-
-
-def full_graph_step_single_gpu(g, k, dev, steps=10, warmup=3):
-    """The N > 1 workload (C3: one full-graph training step, node-range sharded) on ONE GPU, so that the per-N lines
-    of the scaling run can be set against a single-GPU run of the SAME workload (the N = 1 line itself is C2)."""
-    from lgcn_b200 import sharded
-    tr = g.edges("train").to(dev)
-    ops = sharded.CudaOps(tr, g.num_users, g.num_items, k)
-    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
-    trainer = sharded.ShardedTrainer(ops, u0.to(dev), i0.to(dev), sharded.Comm())
-    for _ in range(warmup):
-        trainer.step_sampled(g.num_items, use_graph=False)
-    torch.cuda.synchronize()
-    a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(steps):
-        trainer.step_sampled(g.num_items, use_graph=False)
-    z.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(z) / steps
-    return {"workload": "C3 full-graph training step on 1 GPU (what `--gpus N` runs sharded)", "ms_per_step": ms,
-            "edges_per_s": tr.shape[1] / (ms * 1e-3), "steps": steps, "warmup": warmup}
-
-
-def launches_per_step(k: int, sparse: bool) -> int:
-    if sparse:   # step_begin, mark_negs, 2 replays, K fwd, BPR A+B, K bwd, neg_rows_grad, 2 adam_rows
-        return 1 + 1 + 2 + k + 2 + k + 1 + 2
-    # step_begin + inactive-row fwd + K fwd layers + BPR pass A + pass B + inactive-row bwd + K bwd + clip_adam
-    return 1 + 1 + k + 2 + 1 + k + 1
-
-
 def ncu_traffic(key: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the last committed ncu --set full
     capture (profiles/roofline_traffic.json), or None."""
@@ -349,53 +151,350 @@ def ncu_traffic(key: str):
     return json.load(open(p)).get(key, {}).get("dram_bytes")
 
 
-def graphs_of(model, parts):
-    return [model.graph(d.edge_index) for d in parts]
+def event_pair():
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
-def stage_breakdown(model, opt, parts, graphs, k, dev):
-    """One epoch through the fine-grained C-ABI calls with an event pair around every stage."""
-    from ctypes import byref
-    from lgcn_b200 import _lib
-    L = _lib.lib()
-    s = _lib.stream_ptr(dev)
-    b = opt.buffers
-    uw, iw = model.user_embedding.weight, model.item_embedding.weight
-    names = ["step_begin", "propagate_fwd", "bpr_fwd_bwd", "propagate_bwd", "clip_adam"]
-    evs = {nm: [] for nm in names}
-    loss = torch.empty(1, device=dev)
-    for d, g in zip(parts, graphs):
-        neg = torch.randint(0, model.num_items, (g.num_triplets,), device=dev)
-        b.ensure_triplets(g.num_triplets)
-        reg = 2.0 * 5e-3 / (64.0 * g.num_triplets)
-        calls = [
-            lambda: L.lgcn_step_begin(byref(opt.c), b.accum.data_ptr(), s),
-            lambda: L.lgcn_propagate_fwd(g.ref, uw.data_ptr(), iw.data_ptr(), k, b.final_emb.data_ptr(),
-                                         b.rnorm.data_ptr(), b.work.data_ptr(), b.work.numel() * 4, s),
-            lambda: L.lgcn_bpr_fwd_bwd(g.ref, b.final_emb.data_ptr(), b.rnorm.data_ptr(), neg.data_ptr(),
-                                       b.grad_final.data_ptr(), b.neg_count.data_ptr(), b.trip_scratch.data_ptr(),
-                                       b.accum.data_ptr(), s),
-            lambda: L.lgcn_propagate_bwd(g.ref, b.grad_final.data_ptr(), k, uw.data_ptr(), iw.data_ptr(),
-                                         b.neg_count.data_ptr(), reg, b.grad_e0.data_ptr(), b.accum.data_ptr(),
-                                         b.work.data_ptr(), b.work.numel() * 4, s),
-            lambda: L.lgcn_clip_adam(byref(opt.c), uw.data_ptr(), iw.data_ptr(), model.num_users, model.num_items,
-                                     b.grad_e0.data_ptr(), b.accum.data_ptr(), g.num_triplets, 5e-3, loss.data_ptr(), s),
-        ]
-        for nm, fn in zip(names, calls):
-            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            _lib.check(fn())
-            z.record()
-            evs[nm].append((a, z))
+# --------------------------------------------------------------------------------------------
+# CPU arms: the oracle port timed on the host cores (cpu_baseline blocks and `--impl reference`)
+# --------------------------------------------------------------------------------------------
+
+def cpu_full_graph_sample(nu, ni, train, k, steps, warmup, budget_s):
+    """The reference's CPU implementation of a full-graph training step (oracle port of the PyG gather / scatter op
+    sequence) on a BOUNDED sample of the workload: every `stride`-th train edge, node set unchanged, so that
+    (steps + warmup) sample steps fit `budget_s`.  Returns the cpu_baseline dict + the per-step seconds."""
+    from oracle import reference_path as ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    u0, i0 = synthetic.init_embeddings(nu, ni, 64, 0)
+    gen = torch.Generator().manual_seed(0)
+
+    def run(stride, reps):
+        sub = train[:, ::stride].contiguous()
+        st = ref.TrainState(u0, i0, k)
+        p = int((sub[0] < nu).sum())
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            st.step(sub, torch.randint(0, ni, (p,), generator=gen))
+            ts.append(time.perf_counter() - t0)
+        return sub.shape[1], ts
+
+    _, probe = run(32, 2)                                  # ~1-2 s: sizes the sample
+    per_edge_32 = probe[-1]
+    stride = 32
+    for cand in (16, 8, 4, 2, 1):                          # cost grows roughly linearly with the edge count
+        if per_edge_32 * (32 / cand) * (steps + warmup) <= budget_s:
+            stride = cand
+    edges, ts = run(stride, steps + warmup)
+    ts = ts[warmup:]
+    sec = float(np.mean(ts))
+    return {"value": edges / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"full-table training step on every {stride}th train edge ({edges} of {train.shape[1]} edges, "
+                      f"all {nu + ni} nodes); edges/s of the sample, {len(ts)} timed steps of {sec:.2f} s",
+            "ms_per_sample_step": sec * 1e3, "stride": stride,
+            "full_step_ms_estimate": sec * 1e3 * train.shape[1] / edges}, sec
+
+
+def cpu_cluster_epoch(nu, ni, batches, k):
+    """One WHOLE Cluster-GCN epoch on the CPU oracle: all batches, the hub cluster included, once."""
+    from oracle import reference_path as ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    u0, i0 = synthetic.init_embeddings(nu, ni, 64, 0)
+    st = ref.TrainState(u0, i0, k)
+    gen = torch.Generator().manual_seed(0)
+    total_edges = int(sum(b.shape[1] for b in batches))
+    st.step(batches[1], torch.randint(0, ni, (int((batches[1][0] < nu).sum()),), generator=gen))   # warm-up
+    t0 = time.perf_counter()
+    for ei in batches:
+        st.step(ei, torch.randint(0, ni, (int((ei[0] < nu).sum()),), generator=gen))
+    sec = time.perf_counter() - t0
+    return {"value": total_edges / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"the whole epoch once: all {len(batches)} cluster batches incl. the hub cluster "
+                      f"({max(b.shape[1] for b in batches)} edges), {sec:.1f} s", "epoch_ms": sec * 1e3}
+
+
+# --------------------------------------------------------------------------------------------
+# ours: the full-graph training step (C3 / C5), any N
+# --------------------------------------------------------------------------------------------
+
+def staged_step(trainer, neg, acc):
+    """One eager step with an event pair around every stage (same sequence as ShardedTrainer.step)."""
+    o, k = trainer.ops, trainer.k
+    p2p = getattr(o, "p2p", False)
+
+    def timed(name, fn):
+        a, z = event_pair()
+        a.record(); fn(); z.record()
+        acc.setdefault(name, []).append((a, z))
+    timed("step_begin+prescale", lambda: (o.step_begin(), o.prescale()))
+    timed("exchange", lambda: trainer._gather(o.y[0]))
+    for layer in range(1, k + 1):
+        timed("spmm_fwd_layer", lambda layer=layer: o.fwd_layer(layer))
+        timed("exchange", lambda layer=layer: trainer._gather(o.y[layer] if layer < k else o.final))
+    timed("bpr", lambda: o.bpr(neg))
+    timed("exchange", lambda: trainer._gather(o.zg))
+    for j in range(1, k + 1):
+        timed("spmm_bwd_layer", lambda j=j: o.bwd_layer(j, trainer.bpr_coeff))
+        if j < k:
+            timed("exchange", lambda j=j: trainer._gather(o.zbuf(j)))
+    timed("exchange", lambda: o.allreduce_accum() if p2p else trainer.comm.allreduce(o.accum))
+    timed("clip_adam", lambda: o.clip_adam(trainer.bpr_coeff))
+
+
+def run_full_graph(args):
+    import torch.distributed as dist
+    from lgcn_b200 import sharded
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1 and not dist.is_initialized():
+        # NCCL's own log (INIT lines name the communicator's nranks) goes to stderr; stdout carries the JSON line only
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)                      # NCCL prints its version banner to stdout on first use
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    shape = SHAPE_OF[args.workload]
+    k = synthetic.SHAPES[shape][3]
+    nu, ni, train, graph = shared_train_edges(shape, local, (dist.barrier if world > 1 else (lambda: None)))
+    n, e = nu + ni, train.shape[1]
+    ops = sharded.CudaOps(train, nu, ni, k, device=dev)
+    u0, i0 = synthetic.init_embeddings(nu, ni, 64, 0)
+    trainer = sharded.ShardedTrainer(ops, u0.to(dev), i0.to(dev), sharded.Comm())
+    exchange = ("single GPU, no exchange" if world == 1 else
+                ("fused into the kernel epilogues: " + ("NVLS multicast stores" if ops.multicast else "per-peer NVLink stores")
+                 + " into symmetric memory + one peer barrier per table; no NCCL call inside the step") if ops.p2p else
+                f"NCCL all-gather between kernels (symmetric memory unavailable: {ops.p2p_error})")
+    torch.manual_seed(0)                       # same Philox stream on every rank => identical negatives
+    use_graph = os.environ.get("LGCN_SHARDED_GRAPH", "1") == "1"
+
+    def step():
+        return trainer.step_sampled(ni, use_graph=use_graph)
+
+    for _ in range(max(args.warmup, 5 if use_graph else 0)):      # 3 eager + capture + 1 replay
+        step()
     torch.cuda.synchronize()
-    return {nm: float(sum(a.elapsed_time(z) for a, z in v)) for nm, v in evs.items()}
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    trainer.comm.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = event_pair()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    trainer.comm.barrier()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+    ms_per_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    final_loss = float(loss)
+
+    # ---- per-stage device times: an instrumented EAGER pass right after the timed region (events cannot be placed
+    # inside a CUDA-graph replay); per stage the max over ranks of the mean over `inst` steps
+    inst = max(3, min(args.steps, 10))
+    acc = {}
+    neg = torch.randint(0, ni, (ops.num_triplets,), device=dev)
+    staged_step(trainer, neg, {})
+    torch.cuda.synchronize(); trainer.comm.barrier()
+    for _ in range(inst):
+        staged_step(trainer, neg, acc)
+    torch.cuda.synchronize()
+    stage_ms = {nm: max_over_ranks(sum(a.elapsed_time(z) for a, z in v) / inst) for nm, v in sorted(acc.items())}
+    n_layers = {nm: len(v) // inst for nm, v in acc.items()}
+    layer_ms = (stage_ms["spmm_fwd_layer"] + stage_ms["spmm_bwd_layer"]) / (2 * k)
+
+    # ---- forward propagation alone (BASELINE "propagation edges/s")
+    for _ in range(2):
+        trainer.propagate_only()
+    torch.cuda.synchronize(); trainer.comm.barrier()
+    a, z = event_pair()
+    a.record()
+    for _ in range(5):
+        trainer.propagate_only()
+    z.record()
+    torch.cuda.synchronize()
+    prop_ms = max_over_ranks(a.elapsed_time(z) / 5)
+
+    # ---- e2e: every step uploads this rank's shard of the edge list from PINNED host memory, rebuilds its CSR pair
+    # (K0), re-derives the triplet index, runs one step and reads the loss back
+    sh = ops.shard
+    host_edges = sh.edges.to(torch.int64).pin_memory()
+    host_trip = None if sh.trip_global is None else sh.trip_global.pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+    trainer.drop_graph()
+
+    def e2e_step():
+        ed = host_edges.to(dev, non_blocking=True)
+        tg = None if host_trip is None else host_trip.to(dev, non_blocking=True)
+        ops.load_shard(ed, tg)
+        return float(trainer.step_sampled(ni, use_graph=False).item())
+
+    for _ in range(2):                                              # untimed: the caching allocator gets its blocks
+        e2e_step()
+    torch.cuda.synchronize(); trainer.comm.barrier()
+    a, z = event_pair()
+    a.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    z.record()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks(a.elapsed_time(z) / e2e_steps)
+    h2d = int(host_edges.numel() * 8 + (0 if host_trip is None else host_trip.numel() * 4))
+    h2d_all = torch.tensor([h2d], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(h2d_all)
+
+    peak, peak_src = measured_peak_gbs()
+    b_layer = 2 * n * 256 + 8 * e + 4 * (n + 1)                     # SURVEY.md sec.8(d) contract figure, whole graph
+    roof = {"kernel": "rowtask_kernel<FwdOp|BwdOp> (one propagation layer = one launch per rank; 2K launches per step)",
+            "bound": "hbm", "achieved": b_layer / (layer_ms * 1e-3) / 1e9, "peak": peak * world,
+            "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""), "unit": "GB/s",
+            "traffic": ncu_traffic("rowtask_fwd_layer_r2") if world == 1 and shape == "ml25m" else None,
+            "algorithmic_bytes_per_launch": b_layer, "avg_launch_ms": layer_ms,
+            "share_of_step": 2 * k * layer_ms / sum(stage_ms.values()),
+            "how": f"mean of the {2 * k} layer launches per step over {inst} instrumented eager steps right after the "
+                   "timed region (CUDA events on the launch stream), max over ranks; bytes = compulsory bytes of one "
+                   "layer over the WHOLE graph (all ranks together)",
+            "note": ("the gathered table is L2-resident at this shape, so the layer is bound by the L2 gather rate, not by "
+                     "compulsory HBM bytes: see spmm_full_graph.frac_of_l2_gather_ceiling") if shape == "ml25m" else
+                    "the gathered table (563 MB) does not fit the L2: gathers stream from HBM"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    launches_per_step = 1 + 2 + k + 7 + k + 2 + len(ops.inactive_segs) * 2 + (2 * k + 3 if world > 1 else 0)
+    out = {"metric": METRIC, "value": e / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{args.workload.upper()} full-graph training step (= full-graph epoch), {shape} shape: "
+                                  f"U={nu} I={ni} E_train={e} directed, K={k}, dim=64, fwd+BPR+bwd+clip+Adam, node-range "
+                                  f"sharded over N GPU(s)",
+                      "l2": "tables + activations + CSR (> 1 GB) exceed the 126 MB L2; no explicit flush",
+                      "parallelism": f"node-range x{world}", "exchange": exchange,
+                      "shard_edges_rank0": int(ops.g.num_edges),
+                      "launch": ("one CUDA graph per step (sampling + kernels + peer barriers)"
+                                 if use_graph and not getattr(trainer, "_graph_failed", False) else
+                                 "eager launches" + (f" (graph capture failed: {trainer._graph_error})"
+                                                     if getattr(trainer, "_graph_failed", False) else ""))},
+           "clocks": clk, "gpu_launches": int(args.steps * launches_per_step),
+           "e2e": {"value": e / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": 4 * world,
+                   "note": "per step every rank uploads ITS SHARD of the edge list (pinned int64 [2,E_r] + global triplet "
+                           "numbers) and rebuilds its CSR pair / normalisation (the reference re-derives the normalisation "
+                           "from edge_index in every forward), runs the step eagerly and reads the loss back; "
+                           "h2d bytes are summed over ranks"},
+           "roofline": roof, "stage_ms_per_step": stage_ms, "stage_launches_per_step": n_layers,
+           "propagation": {"ms": prop_ms, "edges_per_s": e * k / (prop_ms * 1e-3), "layers": k},
+           "final_loss": final_loss}
+    return out, dict(nu=nu, ni=ni, train=train, k=k, dev=dev, world=world, rank=rank, trainer=trainer, ops=ops, shape=shape,
+                     graph=graph)
 
 
-def full_graph_propagation(model, train_dev, k, dev, peak):
-    """The SpMM figures of the metric: K-layer fused propagation over the whole train graph."""
+# --------------------------------------------------------------------------------------------
+# named blocks of the N = 1 line
+# --------------------------------------------------------------------------------------------
+
+def block_cluster_gcn_c2(nu, ni, train, k, dev, steps, warmup, with_cpu):
+    """BASELINE configs[1]: one Cluster-GCN epoch (100 METIS parts of the ML-25M-shaped train graph) through train():
+    device-resident batches (`value`), host batches (`e2e`), the persistent step kernel's roofline, the CPU oracle."""
+    from lgcn_b200.data.dataset_handler import ClusterData, ClusterLoader, Data
+    from lgcn_b200.models.light_gcn import LightGCN
+    from lgcn_b200.utils import train_test as tt
+    n = nu + ni
+    cluster = load_partition(train, n, "ml25m")
+    cd = ClusterData(Data(edge_index=train.to(dev), num_nodes=n), NUM_PARTS, cluster=cluster)
+    parts = list(cd.parts)
+    u0, i0 = synthetic.init_embeddings(nu, ni, 64, 0)
+    model = LightGCN(nu, ni, num_layers=k).to(dev)
+    with torch.no_grad():
+        model.user_embedding.weight.copy_(u0)
+        model.item_embedding.weight.copy_(i0)
+    opt = tt.FusedAdam(model)
+    graphs = [model.graph(d.edge_index) for d in parts]
+    live = [d for d, gr in zip(parts, graphs) if gr.num_triplets > 0]
+    grs = [gr for gr in graphs if gr.num_triplets > 0]
+    edges_per_epoch = int(sum(d.edge_index.shape[1] for d in live))
+    loader = ClusterLoader(live, shuffle=True)
+    torch.manual_seed(0)
+    for _ in range(warmup):
+        tt.train(model, opt, loader, dev)
+    torch.cuda.synchronize()
+    a, z = event_pair()
+    a.record()
+    for _ in range(steps):
+        last = tt.train(model, opt, loader, dev)
+    z.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(z) / steps
+    host_parts = [Data(edge_index=d.edge_index.cpu().pin_memory(), num_nodes=n) for d in live]
+
+    class HostLoader:
+        """What the reference's DataLoader hands to train(): batches that live on the HOST (pinned);
+        train() uploads them (utils/train_test.py:87 `batch.to(device)`) every epoch."""
+        def __iter__(self):
+            return iter(host_parts)
+
+    model._graphs.capacity = 4
+    for _ in range(2):
+        tt.train(model, opt, HostLoader(), dev)
+    torch.cuda.synchronize()
+    a, z = event_pair()
+    a.record()
+    for _ in range(steps):
+        tt.train(model, opt, HostLoader(), dev)
+    z.record()
+    torch.cuda.synchronize()
+    e2e_ms = a.elapsed_time(z) / steps
+    peak, _ = measured_peak_gbs()
+    step_bytes = 0
+    for gr in grs:
+        touched = gr.num_active + min(gr.num_triplets, ni)
+        step_bytes += touched * 256 * 6 + gr.num_active * 256 * (2 * (2 * k + 3)) + gr.num_edges * 4 * (2 * k + 4)
+    roof = {"kernel": "epoch_kernel (lgcn_train_steps_sparse: all sparse steps of an epoch in ONE persistent launch)",
+            "bound": "hbm", "achieved": step_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "algorithmic_bytes_per_launch": step_bytes, "avg_launch_ms": ms, "traffic": ncu_traffic("epoch_kernel"),
+            "note": "latency-bound by construction: ~2 k rows / ~7 k edges per step and 2K+2 device-wide barriers per "
+                    "step; duration = the whole epoch (kernel + end-of-epoch flush)"}
+    roof["frac"] = roof["achieved"] / peak
+    blk = {"workload": f"C2 Cluster-GCN training epoch: {NUM_PARTS} METIS parts ({len(live)} non-empty, {edges_per_epoch} "
+                       f"intra-cluster edges), K={k}, fwd+BPR+bwd+clip+Adam per batch",
+           "ms_per_epoch": ms, "value": edges_per_epoch / (ms * 1e-3), "unit": UNIT,
+           "e2e": {"value": edges_per_epoch / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_epoch": e2e_ms,
+                   "h2d_bytes_per_step": int(sum(hp.edge_index.numel() * 8 for hp in host_parts)),
+                   "d2h_bytes_per_step": 4 * len(host_parts),
+                   "note": "train() over HOST (pinned) batches: every epoch uploads all edge lists, rebuilds every "
+                           "batch's normalisation / CSR (one batched K0b call) and reads the losses back"},
+           "roofline": roof, "final_epoch_loss": last, "gpu_launches_per_epoch": 2}
+    if with_cpu:
+        batches = [b for b in cluster_batches_cpu(train, cluster, n) if int((b[0] < nu).sum()) > 0]
+        blk["cpu_baseline"] = cpu_cluster_epoch(nu, ni, batches, k)
+    del model, opt, cd
+    return blk
+
+
+def block_spmm(nu, ni, train, k, dev):
+    """The SpMM figures of the metric: K-layer fused propagation over the whole train graph (single C-ABI call)."""
     from lgcn_b200 import _lib
+    from lgcn_b200.models.light_gcn import LightGCN
     L = _lib.lib()
-    g = model.graph(train_dev)
+    peak, _ = measured_peak_gbs()
+    model = LightGCN(nu, ni, num_layers=k).to(dev)
+    g = model.graph(train.to(dev))
     n, e = g.num_nodes, g.num_edges
     final = torch.empty(n, 64, device=dev)
     work = torch.empty(max(k - 1, 1) * n * 64, device=dev)
@@ -408,16 +507,13 @@ def full_graph_propagation(model, train_dev, k, dev, peak):
         run()
     ts = []
     for _ in range(10):
-        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a, z = event_pair()
         a.record(); run(); z.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(z))
     ms = float(np.median(ts))
-    b_layer = 2 * n * 256 + 8 * e + 4 * (n + 1)                    # SURVEY.md sec.8(d) contract figure
+    b_layer = 2 * n * 256 + 8 * e + 4 * (n + 1)
     gather = e * 264 + n * 256 + 4 * (n + 1)
-    model._graphs.clear()
-    # measured ceiling of this access shape: independent random 256-byte row gathers over a table of the same
-    # size, no index array, no dependent address (csrc/probe.cu) -- what the L2 can deliver at best
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     table = torch.randn(n, 64, device=dev)
     sink = torch.zeros(sms * 6 * 16, device=dev)
@@ -429,7 +525,7 @@ def full_graph_propagation(model, train_dev, k, dev, peak):
         probe()
     pt = []
     for _ in range(5):
-        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a, z = event_pair()
         a.record(); probe(); z.record()
         torch.cuda.synchronize()
         pt.append(a.elapsed_time(z))
@@ -442,18 +538,13 @@ def full_graph_propagation(model, train_dev, k, dev, peak):
                                      "measured live"}
 
 
-# --------------------------------------------------------------------------------------------
-# C4: full-rank evaluation (reported inside the C2 line and on its own with --workload c4)
-# --------------------------------------------------------------------------------------------
-
-def run_c4(args, shape="ml25m"):
+def block_eval_c4(nu, ni, train_dev, test_dev, steps):
+    """BASELINE configs[3]: full-rank evaluation, all users x all items, train-edge mask, top-20."""
     from lgcn_b200.utils import recommend as rec
-    dev = torch.device("cuda:0")
-    g = synthetic.make_graph(shape, seed=0)
-    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
+    dev = train_dev.device
+    u0, i0 = synthetic.init_embeddings(nu, ni, 64, 0)
     ue, ie = u0.to(dev), i0.to(dev)
-    train, test = g.edges("train").to(dev), g.edges("test").to(dev)
-    ptr, idx = rec.exclusion_csr(train, g.num_users)
+    ptr, idx = rec.exclusion_csr(train_dev, nu)
     k = 20
 
     def timed(algo):
@@ -462,161 +553,27 @@ def run_c4(args, shape="ml25m"):
         for _ in range(2):
             run()
         ts = []
-        for _ in range(max(3, min(args.steps, 10))):
-            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(max(3, min(steps, 10))):
+            a, z = event_pair()
             a.record(); run(); z.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(z))
         return float(np.median(ts))
     ms = timed(rec.SCORE_TENSOR)
     ms_ffma = timed(rec.SCORE_FFMA)
-    m = rec.full_rank_eval(ue, ie, train, test, g.num_users, k=k)
-    flop = 2.0 * g.num_users * g.num_items * 64
-    return {"workload": f"C4 full-rank eval {g.num_users} x {g.num_items} x 64, train-edge mask, top-{k}",
-            "ms": ms, "scores_per_s": g.num_users * g.num_items / (ms * 1e-3),
+    m = rec.full_rank_eval(ue, ie, train_dev, test_dev, nu, k=k)
+    flop = 2.0 * nu * ni * 64
+    tf32_peak = measured_bf16_tflops() / 2
+    return {"workload": f"C4 full-rank eval {nu} x {ni} x 64, train-edge mask, top-{k}",
+            "ms": ms, "scores_per_s": nu * ni / (ms * 1e-3),
             "useful_tflops": flop / (ms * 1e-3) / 1e12, "issued_tf32_tflops": 3 * flop / (ms * 1e-3) / 1e12,
-            "tensor_frac_of_tf32_peak": 3 * flop / (ms * 1e-3) / 1e12 / (measured_bf16_tflops() / 2),
+            "roofline": {"kernel": "score_topk_tc_kernel (tcgen05.mma kind::tf32, 3-term hi/lo split)", "bound": "tensor",
+                         "achieved": 3 * flop / (ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": 3 * flop / (ms * 1e-3) / 1e12 / tf32_peak,
+                         "peak_source": "half the measured dense bf16 peak (MEASURED_PEAKS.json)", "traffic": None},
             "math": "tcgen05.mma kind::tf32, 3-term hi/lo split (fp32-level accuracy), fp32 accumulate in TMEM",
             "ffma_kernel_ms": ms_ffma, "recall@20": m["recall"], "ndcg@20": m["ndcg"],
             "users_with_test_items": m["users"], "note": "random-init embeddings: recall/NDCG are chance level"}
-
-
-# --------------------------------------------------------------------------------------------
-# ours, N >= 1 under torchrun (C3): node-range sharded full-graph training step
-# --------------------------------------------------------------------------------------------
-
-def run_c3(args):
-    os.environ["NCCL_DEBUG"] = os.environ.get("LGCN_NCCL_DEBUG", "WARN")      # keep NCCL's banner off stdout
-    import torch.distributed as dist
-    from lgcn_b200 import sharded
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    dev = torch.device(f"cuda:{local}")
-    torch.cuda.set_device(dev)
-    if world > 1 and not dist.is_initialized():
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)                      # NCCL prints its version banner to stdout on first use
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.all_reduce(torch.zeros(1, device=dev))
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
-    shape = os.environ.get("LGCN_BENCH_SHAPE", "ml25m")
-    g = synthetic.make_graph(shape, seed=0)
-    k = synthetic.SHAPES[shape][3]
-    train = g.edges("train")
-    n, e = g.num_nodes, train.shape[1]
-    tr = train.to(dev)
-    ops = sharded.CudaOps(tr, g.num_users, g.num_items, k)
-    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
-    trainer = sharded.ShardedTrainer(ops, u0.to(dev), i0.to(dev), sharded.Comm())
-    exchange = ("single GPU, no exchange" if world == 1 else
-                ("fused into the SpMM epilogue: " + ("NVLS multicast stores" if ops.multicast else "per-peer NVLink stores")
-                 + " into symmetric memory + barrier per layer") if ops.p2p else
-                f"NCCL all-gather between kernels (symmetric memory unavailable: {ops.p2p_error})")
-    p = ops.num_triplets
-    torch.manual_seed(0)                       # same Philox stream on every rank => identical negatives
-
-    use_graph = os.environ.get("LGCN_SHARDED_GRAPH", "0") == "1"     # opt-in until validated at every N
-
-    def step():
-        return trainer.step_sampled(g.num_items, use_graph=use_graph)
-
-    for _ in range(max(args.warmup, 5 if use_graph else 0)):      # 3 eager + capture + 1 replay
-        step()
-    torch.cuda.synchronize()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    trainer.comm.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        loss = step()
-    ev1.record()
-    torch.cuda.synchronize()
-    trainer.comm.barrier()
-    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t) / args.steps
-    clk = clocks.stop() if rank == 0 else None
-
-    # forward propagation alone: per-layer SpMM + all-gather figures of BASELINE config C3
-    for _ in range(2):
-        trainer.propagate_only()
-    torch.cuda.synchronize(); trainer.comm.barrier()
-    a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(5):
-        trainer.propagate_only()
-    z.record()
-    torch.cuda.synchronize()
-    tp = torch.tensor([a.elapsed_time(z) / 5], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-    prop_ms = float(tp)
-
-    # e2e: edge list uploaded from pinned host memory, CSR rebuilt, one step, loss read back
-    host_ei = train.pin_memory()
-    e2e_steps = max(2, min(args.steps, 5))
-    from lgcn_b200 import _lib
-
-    def e2e_step():
-        ei = host_ei.to(dev, non_blocking=True)
-        fresh = _lib.Graph(ei, g.num_users, g.num_items)           # K0 on the uploaded edge list
-        del fresh                                                   # (same content: the trainer keeps its CSR)
-        return float(step().item())
-
-    for _ in range(2):                                              # untimed: the caching allocator gets its blocks
-        e2e_step()
-    torch.cuda.synchronize(); trainer.comm.barrier()
-    a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    z.record()
-    torch.cuda.synchronize()
-    te = torch.tensor([a.elapsed_time(z) / e2e_steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank != 0:
-        return None
-    peak, peak_src = measured_peak_gbs()
-    b_layer = 2 * n * 256 + 8 * e + 4 * (n + 1)
-    roof = {"kernel": "rowtask_kernel<FwdOp> (K-layer propagation incl. all-gathers)", "bound": "hbm",
-            "achieved": k * b_layer / (prop_ms * 1e-3) / 1e9, "peak": peak * world, "peak_source": peak_src + f" x {world} GPUs",
-            "unit": "GB/s", "traffic": None, "algorithmic_bytes_per_launch": k * b_layer, "avg_launch_ms": prop_ms}
-    roof["frac"] = roof["achieved"] / roof["peak"]
-    return {"metric": METRIC, "value": e / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C3 full-graph training step, {shape} shape: U={g.num_users} I={g.num_items} "
-                                   f"E_train={e} directed, K={k}, dim=64, fwd+BPR+bwd+clip+Adam, node-range sharded "
-                                   f"over {world} GPU(s) with all-gather per layer + all-reduce of dL/dfinal",
-                       "l2": "tables + activations + CSR (> 1 GB) exceed the 126 MB L2; no explicit flush",
-                       "parallelism": f"node-range x{world}", "exchange": exchange,
-                       "launch": ("one CUDA graph per step (sampling + kernels + barriers + NCCL)"
-                                  if getattr(trainer, "_graph", None) is not None else
-                                  "eager launches" + (f" (graph capture failed: {trainer._graph_error})"
-                                                      if getattr(trainer, "_graph_failed", False) else ""))},
-            "clocks": clk, "gpu_launches": int(args.steps * (2 + 2 + 2 * k + 2 + 2 * k + 2 + 1)),
-            "e2e": {"value": e / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(train.numel() * 8), "d2h_bytes_per_step": 4,
-                    "note": "edge list uploaded from pinned host memory and CSR rebuilt every step (the reference "
-                            "re-derives the normalisation from edge_index in every forward)"},
-            "roofline": roof, "propagation": {"ms": prop_ms, "edges_per_s": e * k / (prop_ms * 1e-3), "layers": k},
-            "final_loss": float(loss)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -624,54 +581,28 @@ def run_c3(args):
 # --------------------------------------------------------------------------------------------
 
 def run_reference(args):
-    """The reference's CPU implementation of the path = the oracle port (PyG / torch_sparse are not
-    installable offline and /root/reference does not exist on the GPU box), all host threads."""
+    """The reference's CPU implementation of the path = the oracle port (PyG / torch_sparse are not installable
+    offline and /root/reference does not exist on the GPU box), all host threads, on OUR arm's workload: each step is
+    a bounded sample of the full-graph training step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    shape = {"c2": "ml25m", "c1": "ml100k", "c3": os.environ.get("LGCN_BENCH_SHAPE", "ml25m")}[args.workload]
+    shape = SHAPE_OF[args.workload]
     g = synthetic.make_graph(shape, seed=0)
     k = synthetic.SHAPES[shape][3]
     train = g.edges("train")
-    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
-    if args.workload == "c3":
-        from oracle import reference_path as ref
-        torch.set_num_threads(os.cpu_count() or 1)
-        stride = 16
-        sub = train[:, ::stride].contiguous()
-        u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
-        st = ref.TrainState(u0, i0, k)
-        gen = torch.Generator().manual_seed(0)
-        p = int((sub[0] < g.num_users).sum())
-
-        def one():
-            t0 = time.perf_counter()
-            st.step(sub, torch.randint(0, g.num_items, (p,), generator=gen))
-            return time.perf_counter() - t0
-        for _ in range(min(args.warmup, 1)):
-            one()
-        ts = [one() for _ in range(min(args.steps, 5))]
-        sec = float(np.mean(ts))
-        cpu = {"value": sub.shape[1] / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"full-table training step on every {stride}th train edge ({sub.shape[1]} of {train.shape[1]} "
-                         f"edges, N unchanged); edges/s of the sample, {len(ts)} timed steps"}
-        base.update({"value": cpu["value"], "ms_per_step": sec * 1e3 * stride, "scaling": "strong",
-                     "config": {"workload": f"C3 full-graph training step, {shape} shape, K={k}, dim=64; reference CPU path "
-                                            "= oracle port of the PyG gather/scatter op sequence, torch CPU, all host threads"},
-                     "cpu_baseline": cpu,
-                     "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        return base
-    cluster = load_partition(train, g.num_nodes, shape)
-    batches = [b for b in cluster_batches_cpu(train, cluster, g.num_nodes) if int((b[0] < g.num_users).sum()) > 0]
-    cpu = run_cpu_arm(g, batches, k, args.steps, args.warmup)
-    base.update({"value": cpu["value"], "ms_per_step": cpu["epoch_ms_estimate"], "scaling": "weak",
-                 "config": {"workload": f"C2 Cluster-GCN training epoch, {shape} shape, {NUM_PARTS} METIS parts, K={k}, dim=64; "
-                                        "reference CPU path = oracle port of the PyG gather/scatter op sequence "
-                                        "(PyG/torch_sparse not installable offline), torch CPU, all host threads"},
-                 "cpu_baseline": cpu,
-                 "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    return base
+    cpu, sec = cpu_full_graph_sample(g.num_users, g.num_items, train, k, args.steps, args.warmup, budget_s=150.0)
+    return {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload.upper()} full-graph training step (= full-graph epoch), {shape} shape: "
+                                   f"U={g.num_users} I={g.num_items} E_train={train.shape[1]} directed, K={k}, dim=64, "
+                                   f"fwd+BPR+bwd+clip+Adam, node-range sharded over N GPU(s)",
+                       "reference": "CPU path = oracle port of the reference's PyG gather / scatter_add op sequence + BPR + "
+                                    "clip + Adam (torch CPU, all host threads); one step = the bounded sample named in "
+                                    "cpu_baseline.sample; ms_per_step is the measured time of that sample step"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
 def main():
@@ -680,26 +611,51 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3", "c4"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-eval", action="store_true", help="skip the C4 full-rank evaluation section")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5", "c2", "c4"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-extras", action="store_true", help="N = 1: skip the C2 / C4 / SpMM blocks")
     args = ap.parse_args()
-    if args.workload is None:
-        args.workload = "c2" if args.gpus == 1 else "c3"
     if args.impl == "reference":
+        if args.workload in ("c2", "c4"):
+            args.workload = "c3"
         out = run_reference(args)
         if out is not None:
             print(json.dumps(out))
         return
-    if args.workload == "c4":
-        out = run_c4(args)
-    elif args.gpus == 1 and args.workload in ("c1", "c2"):
-        out = run_c2(args)
-        if args.workload == "c2" and not args.no_eval:
-            out["eval_full_rank_c4"] = run_c4(args)
-    else:
-        out = run_c3(args)
-    if out is not None:
+    if args.workload in ("c2", "c4"):                          # standalone blocks (development aid)
+        dev = torch.device("cuda:0")
+        torch.cuda.set_device(dev)
+        g = synthetic.make_graph("ml25m", seed=0)
+        if args.workload == "c2":
+            out = block_cluster_gcn_c2(g.num_users, g.num_items, g.edges("train"), 3, dev, args.steps, args.warmup,
+                                       not args.no_cpu)
+        else:
+            out = block_eval_c4(g.num_users, g.num_items, g.edges("train").to(dev), g.edges("test").to(dev), args.steps)
+        print(json.dumps(out))
+        return
+    out, ctx = run_full_graph(args)
+    import torch.distributed as dist
+    if ctx["world"] == 1 and ctx["shape"] == "ml25m":
+        nu, ni, train, k, dev = ctx["nu"], ctx["ni"], ctx["train"], ctx["k"], ctx["dev"]
+        del ctx["trainer"], ctx["ops"]
+        torch.cuda.empty_cache()
+        if not args.no_cpu:
+            out["cpu_baseline"], _ = cpu_full_graph_sample(nu, ni, train, k, 2, 1, budget_s=25.0)
+        if not args.no_extras:
+            for name, fn in (("spmm_full_graph", lambda: block_spmm(nu, ni, train, k, dev)),
+                             ("cluster_gcn_epoch_c2", lambda: block_cluster_gcn_c2(nu, ni, train, k, dev, args.steps,
+                                                                                   args.warmup, not args.no_cpu)),
+                             ("eval_full_rank_c4", lambda: block_eval_c4(
+                                 nu, ni, train.to(dev), ctx["graph"].edges("test").to(dev), args.steps))):
+                try:
+                    out[name] = fn()
+                except Exception as exc:                        # an extra is never the reason for a missing line
+                    out[name] = {"error": repr(exc)[:300]}
+                torch.cuda.empty_cache()
+    if ctx["world"] > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if ctx["rank"] == 0:
         print(json.dumps(out))
 
 
