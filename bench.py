@@ -72,29 +72,6 @@ def cluster_batches_cpu(train: torch.Tensor, cluster: torch.Tensor, num_nodes: i
     return [e[:, off[p]:off[p + 1]].contiguous() for p in range(NUM_PARTS)]
 
 
-def shared_train_edges(shape: str, local_rank: int, barrier):
-    """(num_users, num_items, train [2,E] int64 CPU tensor).  Under torchrun only local rank 0 generates the
-    synthetic graph (the 10x graph needs ~60 GB of host memory while it is being built); the others read it
-    from /dev/shm after a barrier."""
-    nu, ni = synthetic.SHAPES[shape][0], synthetic.SHAPES[shape][1]
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world == 1:
-        g = synthetic.make_graph(shape, seed=0)
-        return g.num_users, g.num_items, g.edges("train"), g
-    path = f"/dev/shm/lgcn_b200_{shape}_seed0_train_{os.environ.get('MASTER_PORT', '0')}.npy"
-    if local_rank == 0:
-        g = synthetic.make_graph(shape, seed=0)
-        np.save(path + ".tmp.npy", g.edges("train").numpy().astype(np.int32))
-        os.replace(path + ".tmp.npy", path)
-        del g
-    barrier()
-    tr = torch.from_numpy(np.load(path)).to(torch.int64)
-    barrier()
-    if local_rank == 0:
-        os.remove(path)
-    return nu, ni, tr, None
-
-
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -149,6 +126,20 @@ def ncu_traffic(key: str):
     if not os.path.exists(p):
         return None
     return json.load(open(p)).get(key, {}).get("dram_bytes")
+
+
+_REAL_STDOUT = None
+
+
+def emit_line(obj) -> None:
+    """The ONE JSON line on the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, line)
 
 
 def event_pair():
@@ -250,24 +241,20 @@ def run_full_graph(args):
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     if world > 1 and not dist.is_initialized():
-        # NCCL's own log (INIT lines name the communicator's nranks) goes to stderr; stdout carries the JSON line only
+        # NCCL logs to stdout (INIT lines name the communicator's nranks): for the rest of the run fd 1 is stderr, and
+        # the JSON line goes out through the saved descriptor (emit_line), so stdout carries nothing else
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)                      # NCCL prints its version banner to stdout on first use
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.all_reduce(torch.zeros(1, device=dev))
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+        global _REAL_STDOUT
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(torch.zeros(1, device=dev))
+        torch.cuda.synchronize()
     shape = SHAPE_OF[args.workload]
     k = synthetic.SHAPES[shape][3]
-    nu, ni, train, graph = shared_train_edges(shape, local, (dist.barrier if world > 1 else (lambda: None)))
+    nu, ni, train, graph = synthetic.shared_train_edges(shape, local, (dist.barrier if world > 1 else (lambda: None)))
     n, e = nu + ni, train.shape[1]
     ops = sharded.CudaOps(train, nu, ni, k, device=dev)
     u0, i0 = synthetic.init_embeddings(nu, ni, 64, 0)
@@ -401,8 +388,53 @@ def run_full_graph(args):
            "roofline": roof, "stage_ms_per_step": stage_ms, "stage_launches_per_step": n_layers,
            "propagation": {"ms": prop_ms, "edges_per_s": e * k / (prop_ms * 1e-3), "layers": k},
            "final_loss": final_loss}
+    if world > 1:
+        out["exchange_bytes"] = {"per_table_per_gpu_received": int(n * 256 * (world - 1) / world),
+                                 "per_table_per_gpu_sent": int(n * 256 / world),
+                                 "tables_per_step": 2 * k + 2,
+                                 "note": "every produced row (256 B) is stored once by its owner into all copies (NVLS multicast: "
+                                         "the switch replicates); tables per step: y_0..y_{K-1}, final^, z_0..z_{K-1}"}
+    if args.check:
+        out["parity"] = parity_check(trainer, ops, nu, ni, train, k, dev, world, rank)
     return out, dict(nu=nu, ni=ni, train=train, k=k, dev=dev, world=world, rank=rank, trainer=trainer, ops=ops, shape=shape,
                      graph=graph)
+
+
+def parity_check(trainer, ops, nu, ni, train, k, dev, world, rank):
+    """One step from freshly initialised weights on identical negatives against the float64 restatement (rank 0's GPU):
+    loss, dL/dE0 (assembled from every rank's owned rows) and the propagated final rows, normwise."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import fp64_ref
+    u0, i0 = synthetic.init_embeddings(nu, ni, 64, 0)
+    trainer.user_w.copy_(u0.to(dev)); trainer.item_w.copy_(i0.to(dev))
+    ops.m.zero_(); ops.v.zero_(); ops.step_count.zero_()
+    trainer.drop_graph()
+    fin = trainer.propagate_only().clone()
+    gen = torch.Generator().manual_seed(29)
+    neg = torch.randint(0, ni, (ops.num_triplets,), generator=gen).to(dev)
+    loss = float(trainer.step(neg))
+    grad = ops.grad.clone()
+    if world > 1:                                   # every rank contributes its owned rows (the others are stale)
+        own = torch.zeros(nu + ni, dtype=torch.bool, device=dev)
+        for rb, re in trainer.segs:
+            own[rb:re] = True
+        grad[~own] = 0
+        dist.all_reduce(grad)
+    res = None
+    if rank == 0:
+        e0 = torch.cat([u0, i0]).to(dev).double()
+        rl, rgrad, rfinal = fp64_ref.step_loss_and_grad(train.to(dev), e0, k, nu, neg)
+
+        def nw(a, b):
+            return float((a.double() - b).abs().max() / b.abs().max())
+        res = {"against": "float64 restatement of the reference's op sequence on the device (tests/fp64_ref.py)",
+               "loss": loss, "loss_fp64": rl, "loss_rel": abs(loss - rl) / abs(rl),
+               "final_normwise": nw(fin, rfinal), "grad_e0_normwise": nw(grad, rgrad), "tolerance": 1e-5}
+        res["ok"] = bool(res["loss_rel"] < 1e-5 and res["final_normwise"] < 1e-5 and res["grad_e0_normwise"] < 1e-5)
+    if world > 1:
+        dist.barrier()
+    return res
 
 
 # --------------------------------------------------------------------------------------------
@@ -614,6 +646,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c3", "c5", "c2", "c4"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-extras", action="store_true", help="N = 1: skip the C2 / C4 / SpMM blocks")
+    ap.add_argument("--check", action="store_true", help="after the timing: one more step against the float64 restatement "
+                    "(tests/fp64_ref.py) on rank 0's GPU -> `parity` block")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.workload in ("c2", "c4"):
@@ -656,7 +690,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if ctx["rank"] == 0:
-        print(json.dumps(out))
+        emit_line(out)
 
 
 if __name__ == "__main__":

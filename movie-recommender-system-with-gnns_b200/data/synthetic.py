@@ -11,6 +11,7 @@ bit-identical inputs.  This is bench/test plumbing, not a kernel.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Tuple
 
@@ -133,3 +134,27 @@ def hash_partition(num_nodes: int, num_parts: int) -> torch.Tensor:
     x = (x * 2654435761) % (2 ** 32)
     x = x ^ (x >> 15)
     return x % num_parts
+
+
+def shared_train_edges(shape: str, local_rank: int, barrier):
+    """(num_users, num_items, train [2,E] int64 CPU tensor, SyntheticGraph or None).  Under torchrun only local rank 0
+    generates the graph (the 10x graph takes ~90 s and ~15 GB of host memory while it is being built); the other
+    ranks read the train edges from /dev/shm after ``barrier()``."""
+    import numpy as np
+    nu, ni = SHAPES[shape][0], SHAPES[shape][1]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        g = make_graph(shape, seed=0)
+        return g.num_users, g.num_items, g.edges("train"), g
+    path = f"/dev/shm/lgcn_b200_{shape}_seed0_train_{os.environ.get('MASTER_PORT', '0')}.npy"
+    if local_rank == 0:
+        g = make_graph(shape, seed=0)
+        np.save(path + ".tmp.npy", g.edges("train").numpy().astype(np.int32))
+        os.replace(path + ".tmp.npy", path)
+        del g
+    barrier()
+    tr = torch.from_numpy(np.load(path)).to(torch.int64)
+    barrier()
+    if local_rank == 0:
+        os.remove(path)
+    return nu, ni, tr, None

@@ -1,5 +1,6 @@
-"""GPU: the node-range sharded step on the CUDA backend.  world_size 1 always; world_size 2..N over
-NCCL when the box has that many GPUs (gpurun --gpus N)."""
+"""GPU: the node-range sharded step on the CUDA backend.  world_size 1 always; world_size 2..N when the box has
+that many GPUs (gpurun --gpus N): small shapes against the CPU oracle, BASELINE shapes (ML-25M: C3; the 10x graph:
+C5, opt-in) against a float64 restatement on the device (tests/fp64_ref.py)."""
 import os
 import socket
 
@@ -105,3 +106,86 @@ def test_multi_gpu_sharded_step_matches_oracle(tmp_path, world, p2p):
         assert torch.equal(r["uw"], res[0]["uw"]) and torch.equal(r["final"], res[0]["final"])
     uf, itf = ref.forward(res[0]["uw"].double(), res[0]["iw"].double(), train, k)
     assert normwise(res[0]["final"], torch.cat([uf, itf])) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE sizes on N GPUs: forward, loss and dL/dE0 of one sharded step against float64
+# ---------------------------------------------------------------------------------------------
+
+def _full_size_worker(rank, world, port, out_dir, edges_path, nu, ni, k):
+    import numpy as np
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dev = torch.device(f"cuda:{rank}")
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}", device_id=dev)
+    train = torch.from_numpy(np.load(edges_path)).to(torch.int64)
+    u0, i0 = synthetic.init_embeddings(nu, ni, 64, 0)
+    ops = sharded.CudaOps(train, nu, ni, k, device=dev)
+    tr = sharded.ShardedTrainer(ops, u0.to(dev), i0.to(dev), sharded.Comm())
+    fin = tr.propagate_only().clone()
+    # every rank's copy of the exchanged table is complete and bit-identical
+    digest = torch.stack([fin.double().sum(), fin.double().abs().sum(), fin.view(torch.int32).long().sum().double()])
+    all_d = [torch.zeros_like(digest) for _ in range(world)]
+    dist.all_gather(all_d, digest)
+    same = all(torch.equal(d, all_d[0]) for d in all_d)
+    gen = torch.Generator().manual_seed(29)
+    neg = torch.randint(0, ni, (ops.num_triplets,), generator=gen).to(dev)
+    loss = float(tr.step(neg))
+    own = {"segs": tr.segs, "grad": [ops.grad[rb:re].cpu() for rb, re in tr.segs], "loss": loss, "same": same,
+           "p2p": ops.p2p, "multicast": ops.multicast, "shard_edges": int(ops.g.num_edges)}
+    if rank == 0:
+        own["final"] = fin.cpu()
+    torch.save(own, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_full_size(tmp_path, world, shape):
+    import numpy as np
+    import fp64_ref
+    nu, ni, _, k = synthetic.SHAPES[shape]
+    g = synthetic.make_graph(shape, seed=0)
+    train = g.edges("train")
+    del g
+    edges_path = f"/dev/shm/lgcn_test_{shape}_{os.getpid()}.npy"
+    np.save(edges_path, train.numpy().astype(np.int32))
+    try:
+        mp.spawn(_full_size_worker, args=(world, _free_port(), str(tmp_path), edges_path, nu, ni, k), nprocs=world,
+                 join=True)
+    finally:
+        os.remove(edges_path)
+    res = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
+    dev = torch.device("cuda:0")
+    u0, i0 = synthetic.init_embeddings(nu, ni, 64, 0)
+    e0 = torch.cat([u0, i0]).to(dev).double()
+    gen = torch.Generator().manual_seed(29)
+    neg = torch.randint(0, ni, (int((train[0] < nu).sum()),), generator=gen).to(dev)
+    loss, grad, final = fp64_ref.step_loss_and_grad(train.to(dev), e0, k, nu, neg)
+    got_grad = torch.zeros(nu + ni, 64)
+    for r in res:
+        assert r["same"], "ranks hold different copies of the exchanged table"
+        assert abs(r["loss"] - loss) < 1e-5 * abs(loss)
+        for (rb, re), rows in zip(r["segs"], r["grad"]):
+            got_grad[rb:re] = rows
+    e_fin, e_grad = normwise(res[0]["final"], final), normwise(got_grad, grad)
+    print(f"{shape} on {world} GPUs: p2p {res[0]['p2p']} multicast {res[0]['multicast']} shard edges "
+          f"{[r['shard_edges'] for r in res]} of {train.shape[1]}; final normwise {e_fin:.2e}, dL/dE0 normwise {e_grad:.2e}, "
+          f"loss {res[0]['loss']:.7f} vs fp64 {loss:.7f}")
+    assert e_fin < TOL and e_grad < TOL
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_ml25m_step_vs_fp64(tmp_path, world):
+    """BASELINE config C3 at full size on `world` GPUs."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _run_full_size(tmp_path, world, "ml25m")
+
+
+@pytest.mark.skipif(os.environ.get("LGCN_RUN_C5") != "1", reason="set LGCN_RUN_C5=1 (minutes of host time)")
+def test_multi_gpu_c5_10x_graph_step_vs_fp64(tmp_path):
+    """BASELINE config C5 (1.6 M x 0.6 M, 225 M train edges, K = 4) on all GPUs of the box."""
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run_full_size(tmp_path, world, "ml25m_x10")

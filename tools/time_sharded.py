@@ -23,10 +23,16 @@ torch.cuda.set_device(dev)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 shape = os.environ.get("LGCN_BENCH_SHAPE", "ml25m")
-g = synthetic.make_graph(shape, seed=0)
 k = synthetic.SHAPES[shape][3]
-ops = sharded.CudaOps(g.edges("train"), g.num_users, g.num_items, k, device=dev)
-u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
+nu, ni, train, _ = synthetic.shared_train_edges(shape, local, dist.barrier if world > 1 else (lambda: None))
+
+
+class g:                                   # noqa: N801  (the few graph facts used below)
+    num_users, num_items = nu, ni
+
+
+ops = sharded.CudaOps(train, nu, ni, k, device=dev)
+u0, i0 = synthetic.init_embeddings(nu, ni, 64, 0)
 t = sharded.ShardedTrainer(ops, u0.to(dev), i0.to(dev), sharded.Comm())
 torch.manual_seed(0)
 neg = torch.randint(0, g.num_items, (ops.num_triplets,), device=dev)
