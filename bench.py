@@ -254,9 +254,13 @@ def run_full_graph(args):
         torch.cuda.synchronize()
     shape = SHAPE_OF[args.workload]
     k = synthetic.SHAPES[shape][3]
-    nu, ni, train, graph = synthetic.shared_train_edges(shape, local, (dist.barrier if world > 1 else (lambda: None)))
+    # the 10x graph is drawn with the CUDA generator (seconds instead of ~90 s on the host): same recipe, another
+    # seeded graph than the CPU-generated one of the fixtures; its checker (--check) runs on this very edge list
+    gen_dev = dev if shape == "ml25m_x10" else None
+    nu, ni, train, graph = synthetic.shared_train_edges(shape, local, (dist.barrier if world > 1 else (lambda: None)),
+                                                        device=gen_dev)
     n, e = nu + ni, train.shape[1]
-    ops = sharded.CudaOps(train, nu, ni, k, device=dev)
+    ops = sharded.CudaOps(train.to(dev), nu, ni, k, device=dev)      # the shard is cut on the device
     u0, i0 = synthetic.init_embeddings(nu, ni, 64, 0)
     trainer = sharded.ShardedTrainer(ops, u0.to(dev), i0.to(dev), sharded.Comm())
     exchange = ("single GPU, no exchange" if world == 1 else
@@ -323,8 +327,8 @@ def run_full_graph(args):
     # ---- e2e: every step uploads this rank's shard of the edge list from PINNED host memory, rebuilds its CSR pair
     # (K0), re-derives the triplet index, runs one step and reads the loss back
     sh = ops.shard
-    host_edges = sh.edges.to(torch.int64).pin_memory()
-    host_trip = None if sh.trip_global is None else sh.trip_global.pin_memory()
+    host_edges = sh.edges.cpu().to(torch.int64).pin_memory()
+    host_trip = None if sh.trip_global is None else sh.trip_global.cpu().pin_memory()
     e2e_steps = max(2, min(args.steps, 5))
     trainer.drop_graph()
 
@@ -367,7 +371,8 @@ def run_full_graph(args):
     launches_per_step = 1 + 2 + k + 7 + k + 2 + len(ops.inactive_segs) * 2 + (2 * k + 3 if world > 1 else 0)
     out = {"metric": METRIC, "value": e / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic" + (" (CUDA-generated seeded graph)" if gen_dev is not None else ""),
            "config": {"workload": f"{args.workload.upper()} full-graph training step (= full-graph epoch), {shape} shape: "
                                   f"U={nu} I={ni} E_train={e} directed, K={k}, dim=64, fwd+BPR+bwd+clip+Adam, node-range "
                                   f"sharded over N GPU(s)",
@@ -394,6 +399,12 @@ def run_full_graph(args):
                                  "tables_per_step": 2 * k + 2,
                                  "note": "every produced row (256 B) is stored once by its owner into all copies (NVLS multicast: "
                                          "the switch replicates); tables per step: y_0..y_{K-1}, final^, z_0..z_{K-1}"}
+    if world > 1 and shape == "ml25m":
+        try:
+            out["eval_full_rank_c4_sharded"] = block_eval_c4_sharded(nu, ni, ops.edge_index, world, rank, args.steps,
+                                                                     max_over_ranks, trainer.comm.barrier)
+        except Exception as exc:                                # every rank takes the same path: no rank is left waiting
+            out["eval_full_rank_c4_sharded"] = {"error": repr(exc)[:300]}
     if args.check:
         out["parity"] = parity_check(trainer, ops, nu, ni, train, k, dev, world, rank)
     return out, dict(nu=nu, ni=ni, train=train, k=k, dev=dev, world=world, rank=rank, trainer=trainer, ops=ops, shape=shape,
@@ -606,6 +617,37 @@ def block_eval_c4(nu, ni, train_dev, test_dev, steps):
             "math": "tcgen05.mma kind::tf32, 3-term hi/lo split (fp32-level accuracy), fp32 accumulate in TMEM",
             "ffma_kernel_ms": ms_ffma, "recall@20": m["recall"], "ndcg@20": m["ndcg"],
             "users_with_test_items": m["users"], "note": "random-init embeddings: recall/NDCG are chance level"}
+
+
+def block_eval_c4_sharded(nu, ni, train_dev, world, rank, steps, max_over_ranks, barrier):
+    """BASELINE configs[3] over the N GPUs of the job: rank r scores its user range against the
+    replicated item table (train-edge mask, top-20); no collective on the data path.  Time = max over ranks."""
+    from lgcn_b200.utils import recommend as rec
+    dev = train_dev.device
+    u0, i0 = synthetic.init_embeddings(nu, ni, 64, 0)
+    ue, ie = u0.to(dev), i0.to(dev)
+    ptr, idx = rec.exclusion_csr(train_dev, nu)
+    lo, hi = rec.user_ranges(nu, world)[rank]
+
+    def run():
+        return rec.score_topk(ue, ie, 20, True, ptr, idx, lo, hi)
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize(); barrier()
+    reps = max(3, min(steps, 10))
+    a, z = event_pair()
+    a.record()
+    for _ in range(reps):
+        top, _ = run()
+    z.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(a.elapsed_time(z) / reps)
+    digest = max_over_ranks(float(top.to(torch.float64).sum())) if world == 1 else None
+    flop = 2.0 * nu * ni * 64
+    return {"workload": f"C4 full-rank eval {nu} x {ni} x 64, train-edge mask, top-20, users split over {world} GPU(s) "
+                        f"in equal ranges (multiples of the 128-user CTA tile)",
+            "ms": ms, "scores_per_s": nu * ni / (ms * 1e-3), "useful_tflops": flop / (ms * 1e-3) / 1e12,
+            "issued_tf32_tflops": 3 * flop / (ms * 1e-3) / 1e12, "users_rank0": hi - lo, "digest": digest}
 
 
 # --------------------------------------------------------------------------------------------

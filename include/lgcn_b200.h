@@ -408,6 +408,15 @@ int lgcn_cluster_extract(const int64_t *edge_index, int64_t num_edges, int64_t n
                          const int64_t *cluster, int64_t num_parts, int64_t *out_edges,
                          int64_t *part_ptr, void *workspace, size_t workspace_bytes, void *stream);
 
+/* to_undirected (PyG 2.4.0 utils/undirected.py:to_undirected + coalesce, called at
+ * data/dataset_handler.py:141): both directions of every edge of edge_index [2,E] int64 (device), sorted by
+ * (row, col), duplicates dropped.  out_edges: device int64, 4*E cells; on return cells [0,count) hold the rows
+ * and [count, 2*count) the columns, i.e. a contiguous [2,count] tensor.  *count_out (HOST) = number of distinct
+ * directed edges.  Ids outside [0,num_nodes) are rejected (LGCN_E_INVALID).  Synchronises the stream. */
+size_t lgcn_to_undirected_workspace_bytes(int64_t num_edges);
+int lgcn_to_undirected(const int64_t *edge_index, int64_t num_edges, int64_t num_nodes, int64_t *out_edges,
+                       int64_t *count_out, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- K5: scoring GEMM + train-edge mask + top-k ------------------------------------------- */
 
 /* For users [u_begin,u_end): score(u,i) = <U[u],I[i]> (rows optionally L2-normalised first, as

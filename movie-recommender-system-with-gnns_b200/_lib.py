@@ -32,6 +32,7 @@ EXPORTS = [
     "lgcn_train_steps_workspace_bytes", "lgcn_train_steps_sparse", "lgcn_probe_gather",
     "lgcn_score_topk_workspace_bytes", "lgcn_upload_lists",
     "lgcn_bpr_owner", "lgcn_fwd_layer_ex", "lgcn_triplet_index", "lgcn_graph_remap_triplets", "lgcn_peer_allreduce4",
+    "lgcn_to_undirected_workspace_bytes", "lgcn_to_undirected",
 ]
 
 
@@ -124,6 +125,9 @@ def lib():
     L.lgcn_cluster_extract_workspace_bytes.restype = c_size_t
     L.lgcn_cluster_extract.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                        c_size_t, c_void_p]
+    L.lgcn_to_undirected_workspace_bytes.argtypes = [c_int64]
+    L.lgcn_to_undirected_workspace_bytes.restype = c_size_t
+    L.lgcn_to_undirected.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     L.lgcn_score_topk.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int,
                                   c_void_p, c_void_p, c_void_p]
     L.lgcn_score_topk_ex.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int,
@@ -164,7 +168,7 @@ def lib():
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("lgcn_last_error", "lgcn_cluster_extract_workspace_bytes", "lgcn_train_steps_workspace_bytes",
-                        "lgcn_score_topk_workspace_bytes"):
+                        "lgcn_score_topk_workspace_bytes", "lgcn_to_undirected_workspace_bytes"):
             fn.restype = c_int
     _lib = L
     return L

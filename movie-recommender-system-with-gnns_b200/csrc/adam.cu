@@ -59,13 +59,15 @@ extern "C" int lgcn_clip_adam_rows(const lgcn_adam *opt, float *user_w, float *i
                  "clip_adam: bad row range");
     const size_t user_vec = (size_t)num_users * lgcn::D4;
     const size_t vb = (size_t)row_begin * lgcn::D4, ve = (size_t)row_end * lgcn::D4;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    static int sms_of[64];                               // SM count, cached per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = dev >= 0 && dev < 64 ? dev : 0;
+    if (sms_of[dev] == 0) {
+        cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (sms_of[dev] <= 0) sms_of[dev] = 148;
     }
+    const int sms = sms_of[dev];
     const int64_t want = (int64_t)((ve - vb + 255) / 256);
     const int grid = (int)(want < (int64_t)sms * 8 ? (want > 0 ? want : 1) : (int64_t)sms * 8);
     lgcn::clip_adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(

@@ -107,6 +107,70 @@ static ClusterWs cluster_carve(void *base, int64_t N, int64_t E, int64_t P) {
     return w;
 }
 
+
+// ---- to_undirected (PyG 2.4.0 utils/undirected.py + coalesce; /root/reference/data/dataset_handler.py:141) ----
+// Both directions of every edge, sorted by (row, col), duplicates dropped:
+//   1. keys[i] = r*N + c, keys[E + i] = c*N + r       2. one keys-only 64-bit radix sort
+//   3. head flags (key != predecessor) scanned to output slots      4. decode the kept keys.
+// Integer work, bit-exact; the count of distinct edges is data-dependent, so the decode kernel reads it from the
+// scan's last cell and writes rows at [0,count) and columns at [count, 2*count) of the flat output.
+__global__ void undirected_key_kernel(const int64_t *__restrict__ ei, int64_t E, int64_t N,
+                                      unsigned long long *__restrict__ keys, int *bad) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int64_t r = ei[e], c = ei[E + e];
+    if (r < 0 || r >= N || c < 0 || c >= N) { atomicAdd(bad, 1); r = c = 0; }
+    keys[e] = (unsigned long long)r * (unsigned long long)N + (unsigned long long)c;
+    keys[E + e] = (unsigned long long)c * (unsigned long long)N + (unsigned long long)r;
+}
+
+struct HeadFlag {
+    const unsigned long long *k;
+    int64_t n;
+    __host__ __device__ int operator()(int i) const { return i < n && (i == 0 || k[i] != k[i - 1]) ? 1 : 0; }
+};
+
+__global__ void undirected_decode_kernel(const unsigned long long *__restrict__ sorted, const int *__restrict__ slot,
+                                         int64_t M, int64_t N, int64_t *__restrict__ out, int64_t *count_dev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const int64_t count = slot[M];
+    if (i == 0) *count_dev = count;
+    if (slot[i + 1] == slot[i]) return;                  // duplicate of its predecessor
+    const unsigned long long k = sorted[i], n = (unsigned long long)N;
+    out[slot[i]] = (int64_t)(k / n);
+    out[count + slot[i]] = (int64_t)(k % n);
+}
+
+struct UndirWs {
+    unsigned long long *keys, *keys_sorted;
+    int *slot, *bad;
+    int64_t *count;
+    void *cub_temp;
+    size_t cub_bytes, total;
+};
+
+static UndirWs undir_carve(void *base, int64_t E) {
+    UndirWs w{};
+    char *p = (char *)base;
+    auto take = [&](size_t bytes) { char *q = p; p += al256(bytes); return q; };
+    const int64_t M = 2 * E;
+    const size_t kb = sizeof(unsigned long long) * (size_t)(M > 0 ? M : 1);
+    w.keys = (unsigned long long *)take(kb); w.keys_sorted = (unsigned long long *)take(kb);
+    w.slot = (int *)take(sizeof(int) * (size_t)(M + 1));
+    w.bad = (int *)take(256); w.count = (int64_t *)take(256);
+    size_t a = 0, b = 0;
+    unsigned long long *k64 = nullptr; int *k = nullptr;
+    cub::DeviceRadixSort::SortKeys(nullptr, a, k64, k64, (int)M, 0, 64);
+    cub::CountingInputIterator<int> idx(0);
+    cub::TransformInputIterator<int, HeadFlag, cub::CountingInputIterator<int>> flags(idx, HeadFlag{nullptr, 0});
+    cub::DeviceScan::ExclusiveSum(nullptr, b, flags, k, (int)(M + 1));
+    w.cub_bytes = al256(a > b ? a : b) + 256;
+    w.cub_temp = take(w.cub_bytes);
+    w.total = (size_t)(p - (char *)base);
+    return w;
+}
+
 }  // namespace lgcn
 
 extern "C" size_t lgcn_cluster_extract_workspace_bytes(int64_t N, int64_t E, int64_t P) {
@@ -152,5 +216,47 @@ extern "C" int lgcn_cluster_extract(const int64_t *edge_index, int64_t E, int64_
     LGCN_CUDA(cudaMemcpyAsync(&bad, w.bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     LGCN_CUDA(cudaStreamSynchronize(st));
     LGCN_REQUIRE(bad == 0, LGCN_E_INVALID, "cluster_extract: %d ids outside [0,N) or parts outside [0,P)", bad);
+    return LGCN_OK;
+}
+
+extern "C" size_t lgcn_to_undirected_workspace_bytes(int64_t E) {
+    if (E < 0 || 2 * E + 1 >= INT32_MAX) return 0;
+    return lgcn::undir_carve(nullptr, E).total;
+}
+
+extern "C" int lgcn_to_undirected(const int64_t *edge_index, int64_t E, int64_t N, int64_t *out_edges,
+                                  int64_t *count_out, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace lgcn;
+    cudaStream_t st = (cudaStream_t)stream;
+    LGCN_REQUIRE(count_out && workspace && (E == 0 || (edge_index && out_edges)), LGCN_E_INVALID,
+                 "to_undirected: null argument");
+    LGCN_REQUIRE(N > 0 && E >= 0, LGCN_E_INVALID, "to_undirected: bad sizes");
+    LGCN_REQUIRE(N < INT32_MAX && 2 * E + 1 < INT32_MAX, LGCN_E_RANGE, "to_undirected: N / 2E exceed int32");
+    *count_out = 0;
+    if (E == 0) return LGCN_OK;
+    UndirWs w = undir_carve(workspace, E);
+    LGCN_REQUIRE(workspace_bytes >= w.total, LGCN_E_WORKSPACE, "to_undirected: workspace %zu < %zu", workspace_bytes,
+                 w.total);
+    const int T = 256;
+    const int64_t M = 2 * E;
+    LGCN_CUDA(cudaMemsetAsync(w.bad, 0, sizeof(int), st));
+    undirected_key_kernel<<<cdiv(E, T), T, 0, st>>>(edge_index, E, N, w.keys, w.bad);
+    LGCN_LAUNCH_CHECK();
+    size_t tb = w.cub_bytes;
+    LGCN_CUDA(cub::DeviceRadixSort::SortKeys(w.cub_temp, tb, w.keys, w.keys_sorted, (int)M, 0,
+                                             bits64((unsigned long long)N * (unsigned long long)N), st));
+    cub::CountingInputIterator<int> idx(0);
+    cub::TransformInputIterator<int, HeadFlag, cub::CountingInputIterator<int>> flags(idx, HeadFlag{w.keys_sorted, M});
+    tb = w.cub_bytes;
+    LGCN_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, flags, w.slot, (int)(M + 1), st));
+    undirected_decode_kernel<<<cdiv(M, T), T, 0, st>>>(w.keys_sorted, w.slot, M, N, out_edges, w.count);
+    LGCN_LAUNCH_CHECK();
+    int bad = 0;
+    int64_t count = 0;
+    LGCN_CUDA(cudaMemcpyAsync(&bad, w.bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LGCN_CUDA(cudaMemcpyAsync(&count, w.count, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    LGCN_CUDA(cudaStreamSynchronize(st));
+    LGCN_REQUIRE(bad == 0, LGCN_E_INVALID, "to_undirected: %d node ids outside [0,N)", bad);
+    *count_out = count;
     return LGCN_OK;
 }

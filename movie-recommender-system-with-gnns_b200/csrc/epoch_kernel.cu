@@ -1145,19 +1145,23 @@ extern "C" int lgcn_train_steps_sparse(const lgcn_graph *graphs, int64_t num_ste
     static const bool want_prof = getenv("LGCN_EPOCH_PROF") != nullptr;   // tools/epoch_breakdown.py
     a.prof = want_prof ? (long long *)(state + 512) : nullptr;
 
-    static int grid = 0, num_sms = 0, ctas_per_sm = 0;
-    if (grid == 0) {
-        int dev = 0, sms = 0, per_sm = 0, coop = 0;
-        LGCN_CUDA(cudaGetDevice(&dev));
+    // launch geometry, cached per device (a process may drive several GPUs)
+    static int grid_of[64], sms_of[64], per_sm_of[64];
+    int dev = 0;
+    LGCN_CUDA(cudaGetDevice(&dev));
+    LGCN_REQUIRE(dev >= 0 && dev < 64, LGCN_E_INVALID, "train_steps_sparse: device ordinal %d", dev);
+    if (grid_of[dev] == 0) {
+        int sms = 0, per_sm = 0, coop = 0;
         LGCN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         LGCN_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
         LGCN_REQUIRE(coop, LGCN_E_CUDA, "train_steps_sparse: device does not support cooperative launches");
         LGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epoch_kernel, EP_THREADS, 0));
         LGCN_REQUIRE(per_sm >= 1, LGCN_E_CUDA, "train_steps_sparse: kernel does not fit on an SM");
-        num_sms = sms;
-        ctas_per_sm = per_sm >= EP_CTAS_PER_SM ? EP_CTAS_PER_SM : per_sm;
-        grid = sms * ctas_per_sm;                         // the cooperative launch fills every SM with ctas_per_sm CTAs
+        sms_of[dev] = sms;
+        per_sm_of[dev] = per_sm >= EP_CTAS_PER_SM ? EP_CTAS_PER_SM : per_sm;
+        grid_of[dev] = sms * per_sm_of[dev];             // the cooperative launch fills every SM with ctas_per_sm CTAs
     }
+    const int grid = grid_of[dev], num_sms = sms_of[dev], ctas_per_sm = per_sm_of[dev];
     // helpers: whole SMs (LGCN_EPOCH_HELPER_SMS: tuning aid)
     static const int hsms_env = getenv("LGCN_EPOCH_HELPER_SMS") ? atoi(getenv("LGCN_EPOCH_HELPER_SMS")) : -1;
     int helper_sms = hsms_env >= 1 ? hsms_env : (num_sms * 7) / 20;

@@ -14,6 +14,7 @@ Python loop of boolean masks; the batches are views into one device buffer and c
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Dict, Iterator, List, Optional, Tuple
 
@@ -68,12 +69,42 @@ class ClusterLoader:
 
 def to_undirected(edge_index: torch.Tensor, num_nodes: Optional[int] = None) -> torch.Tensor:
     """PyG ``to_undirected`` (dataset_handler.py:141): both directions, sorted by (row, col),
-    duplicates dropped.  One 64-bit key sort on whatever device holds the edges."""
-    row = torch.cat([edge_index[0], edge_index[1]])
-    col = torch.cat([edge_index[1], edge_index[0]])
-    n = int(max(row.max(), col.max())) + 1 if num_nodes is None else num_nodes
-    key = torch.unique(row * n + col)            # sorted + deduplicated
-    return torch.stack([key // n, key % n])
+    duplicates dropped -- ``lgcn_to_undirected``: key build, one 64-bit radix sort, head-flag scan and
+    compaction on the device (no CPU path: the edges must be a CUDA tensor)."""
+    require_cuda(edge_index, "edge_index", torch.int64)
+    ei = edge_index.contiguous()
+    dev = ei.device
+    e = ei.size(1)
+    if e == 0:
+        return torch.empty(2, 0, dtype=torch.int64, device=dev)
+    n = int(ei.max()) + 1 if num_nodes is None else int(num_nodes)
+    out = torch.empty(4 * e, dtype=torch.int64, device=dev)
+    ws = torch.empty(lib().lgcn_to_undirected_workspace_bytes(e), dtype=torch.uint8, device=dev)
+    count = ctypes.c_int64(0)
+    check(lib().lgcn_to_undirected(ei.data_ptr(), e, n, out.data_ptr(), ctypes.addressof(count), ws.data_ptr(),
+                                   ws.numel(), stream_ptr(dev)))
+    return out[:2 * count.value].view(2, count.value)
+
+
+def shuffle_split(n: int, train_size: Optional[float] = None, test_size: Optional[float] = None
+                  ) -> Tuple[np.ndarray, np.ndarray]:
+    """``sklearn.model_selection.train_test_split(np.arange(n), train_size=..|test_size=.., shuffle=True)`` as the
+    reference calls it (dataset_handler.py:167-168), restated: ``n_test = ceil(test_size*n)`` / ``n_train =
+    floor(train_size*n)`` (the missing one is the complement), ONE permutation from numpy's global RandomState,
+    test = its first n_test positions, train = the next n_train.  Consumes the same random stream as sklearn, so
+    a seeded run splits identically (tests/test_host_logic_cpu.py compares with sklearn itself and the fixture)."""
+    if (train_size is None) == (test_size is None):
+        raise ValueError("give exactly one of train_size / test_size")
+    if test_size is not None:
+        n_test = int(np.ceil(test_size * n))
+        n_train = n - n_test
+    else:
+        n_train = int(np.floor(train_size * n))
+        n_test = n - n_train
+    if n_train <= 0 or n_test <= 0:
+        raise ValueError(f"With n_samples={n}, the resulting train/test set would be empty")
+    perm = np.random.permutation(n)
+    return perm[n_test:n_test + n_train], perm[:n_test]
 
 
 def metis_partition(edge_index: torch.Tensor, num_nodes: int, num_parts: int) -> torch.Tensor:
@@ -154,13 +185,12 @@ class GraphDataHandler:
 
     def _indices(self, train_size: float):
         if self._split is None:
-            # dataset_handler.py:167-172: shuffle split 90/5/5 over DIRECTED edge positions, sorted
-            e = self.edge_index.shape[1]
-            perm = np.random.permutation(e)
-            n_train = int(round(e * train_size))
-            n_val = (e - n_train) // 2
-            self._split = (np.sort(perm[:n_train]), np.sort(perm[n_train:n_train + n_val]),
-                           np.sort(perm[n_train + n_val:]))
+            # dataset_handler.py:167-172: two shuffle splits over DIRECTED edge positions (90 % train, the rest halved
+            # into val / test), each index set sorted
+            train, val_test = shuffle_split(self.edge_index.shape[1], train_size=train_size)
+            vt_train, vt_test = shuffle_split(len(val_test), test_size=0.5)
+            val, test = val_test[vt_train], val_test[vt_test]
+            self._split = (np.sort(train), np.sort(val), np.sort(test))
         return self._split
 
     def get_datasets(self, train_size: float = 0.9) -> Tuple[Data, Data, Data]:

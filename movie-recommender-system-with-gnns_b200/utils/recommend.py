@@ -60,30 +60,74 @@ def exclusion_csr(train_edge_index: torch.Tensor, num_users: int) -> Tuple[torch
 
 def full_rank_eval(user_emb: torch.Tensor, item_emb: torch.Tensor, train_edge_index: torch.Tensor,
                    test_edge_index: torch.Tensor, num_users: int, k: int = 20, normalize: bool = True,
-                   user_block: int = 32768) -> Dict[str, float]:
+                   user_block: int = 32768, u_begin: int = 0, u_end: Optional[int] = None,
+                   allreduce=None) -> Dict[str, float]:
     """BASELINE config C4: all-user x all-item scoring, train items masked, recall@k / NDCG@k against
-    the held-out user->movie edges.  The score matrix is never materialised."""
+    the held-out user->movie edges.  The score matrix is never materialised.
+
+    Multi-GPU ("embarrassingly parallel over user ranges; items replicated"): every rank scores
+    its own user range [u_begin, u_end) and ``allreduce`` (a callable that sums a float64 tensor over the ranks
+    in place) combines the three partial sums -- see ``sharded_full_rank_eval``."""
+    u_end = num_users if u_end is None else u_end
+    dev = user_emb.device
     ptr, idx = exclusion_csr(train_edge_index, num_users)
     tops = []
-    for b in range(0, num_users, user_block):
-        tops.append(score_topk(user_emb, item_emb, k, normalize, ptr, idx, b, min(num_users, b + user_block))[0])
-    top = torch.cat(tops).to(torch.int64)
+    for b in range(u_begin, u_end, user_block):
+        tops.append(score_topk(user_emb, item_emb, k, normalize, ptr, idx, b, min(u_end, b + user_block))[0])
+    top = torch.cat(tops).to(torch.int64) if tops else torch.empty(0, k, dtype=torch.int64, device=dev)
+    nloc = u_end - u_begin
     tptr, tidx = exclusion_csr(test_edge_index, num_users)
-    cnt = (tptr[1:] - tptr[:-1])
+    cnt_all = (tptr[1:] - tptr[:-1])
+    cnt = cnt_all[u_begin:u_end]
     # membership test: (user, item) keys of the held-out edges, sorted
     n_items = item_emb.size(0)
-    owner = torch.repeat_interleave(torch.arange(num_users, device=top.device), cnt)
+    owner = torch.repeat_interleave(torch.arange(num_users, device=dev), cnt_all)
     truth = torch.sort(owner * n_items + tidx.to(torch.int64))[0]
-    keys = torch.arange(num_users, device=top.device).unsqueeze(1) * n_items + top.clamp(min=0)
+    keys = torch.arange(u_begin, u_end, device=dev).unsqueeze(1) * n_items + top.clamp(min=0)
     pos = torch.searchsorted(truth, keys.reshape(-1)).clamp(max=max(truth.numel() - 1, 0))
     hit = ((truth[pos] == keys.reshape(-1)) if truth.numel() else torch.zeros_like(pos, dtype=torch.bool))
-    hit = (hit.reshape(num_users, k) & (top >= 0)).to(torch.float64)
-    disc = 1.0 / torch.log2(torch.arange(2, k + 2, dtype=torch.float64, device=top.device))
+    hit = (hit.reshape(nloc, k) & (top >= 0)).to(torch.float64)
+    disc = 1.0 / torch.log2(torch.arange(2, k + 2, dtype=torch.float64, device=dev))
     has = cnt > 0
-    recall = (hit.sum(1)[has] / cnt[has]).mean().item() if has.any() else 0.0
     idcg = torch.cumsum(disc, 0)[(cnt.clamp(max=k) - 1).clamp(min=0)]
-    ndcg = ((hit * disc).sum(1)[has] / idcg[has]).mean().item() if has.any() else 0.0
-    return {"recall": recall, "ndcg": ndcg, "users": int(has.sum())}
+    sums = torch.zeros(3, dtype=torch.float64, device=dev)
+    if bool(has.any()):
+        sums[0] = (hit.sum(1)[has] / cnt[has]).sum()
+        sums[1] = ((hit * disc).sum(1)[has] / idcg[has]).sum()
+        sums[2] = has.sum()
+    if allreduce is not None:
+        allreduce(sums)
+    users = int(sums[2])
+    return {"recall": float(sums[0]) / users if users else 0.0, "ndcg": float(sums[1]) / users if users else 0.0,
+            "users": users}
+
+
+def user_ranges(num_users: int, world: int, tile: int = 128) -> List[Tuple[int, int]]:
+    """Equal user ranges for sharded scoring, cut at multiples of the scoring kernel's 128-user CTA tile (every user
+    costs the same: one pass over all items)."""
+    tiles = (num_users + tile - 1) // tile
+    cuts = [min(num_users, ((tiles * r) // world) * tile) for r in range(world)] + [num_users]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def sharded_full_rank_eval(user_emb: torch.Tensor, item_emb: torch.Tensor, train_edge_index: torch.Tensor,
+                           test_edge_index: torch.Tensor, num_users: int, k: int = 20, normalize: bool = True,
+                           group=None) -> Dict[str, float]:
+    """C4 over the GPUs of a ``torch.distributed`` job: rank r scores users ``user_ranges(...)[r]`` against the
+    replicated item table; one all-reduce of three doubles yields the same recall / NDCG on every rank."""
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if on else 1
+    rank = dist.get_rank(group) if on else 0
+    lo, hi = user_ranges(num_users, world)[rank]
+
+    def allreduce(t):
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    out = full_rank_eval(user_emb, item_emb, train_edge_index, test_edge_index, num_users, k, normalize,
+                         u_begin=lo, u_end=hi, allreduce=allreduce)
+    out["user_range"] = (lo, hi)
+    return out
 
 
 def recommend_from_user(model: torch.nn.Module, user_id: int, data_handler: Any,

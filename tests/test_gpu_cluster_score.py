@@ -1,4 +1,6 @@
 """GPU parity: Cluster-GCN extraction (K4, bit-exact) and fused scoring + mask + top-k (K5)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -79,6 +81,60 @@ def test_metis_partition_same_call_as_oracle_and_loader_contract():
     want = ref.cluster_batches(train, n, part, 10)
     got = {d.edge_index.shape[1] for d in loader.dataset}
     assert got == {w.shape[1] for w in want}
+
+
+def test_movielens_handler_csv_pipeline_matches_reference_fixture(golden, tmp_path, monkeypatch):
+    """The product's MovieLensDataHandler end to end on the CSV the reference itself ingested
+    (oracle/gen_golden.py::gen_cluster_pipeline; data/dataset_handler.py:98-141,160-199,256-288): rating filter, id maps
+    in order of first appearance, to_undirected (device kernel), the seeded 90/5/5 split, METIS, the cluster batches."""
+    import pandas as pd
+    g = golden("cluster_pipeline.npz")
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("data/movielens-25m")
+    rp, mp = "data/movielens-25m/ratings.csv", "data/movielens-25m/movies.csv"
+    pd.DataFrame({"userId": g["csv_user"], "movieId": g["csv_movie"], "rating": g["csv_rating"], "timestamp": 0}
+                 ).to_csv(rp, index=False)
+    all_movies = np.unique(g["csv_movie"])
+    pd.DataFrame({"movieId": all_movies, "title": [f"Movie {x}" for x in all_movies], "genres": "x"}).to_csv(mp, index=False)
+    np.random.seed(2024)
+    h = dh.MovieLensDataHandler(rp, mp, device=DEV)
+    assert (h.num_users, h.num_movies) == (int(g["num_users"]), int(g["num_movies"]))
+    assert h.get_num_users_items() == (int(g["num_users"]), int(g["num_movies"]))
+    assert list(h.user_id_map.keys()) == g["user_id_keys"].tolist() and list(h.user_id_map.values()) == g["user_id_vals"].tolist()
+    assert list(h.movie_id_map.keys()) == g["movie_id_keys"].tolist() and list(h.movie_id_map.values()) == g["movie_id_vals"].tolist()
+    assert h.id_movie_map[h.movie_id_map[int(g["movie_id_keys"][5])]] == int(g["movie_id_keys"][5])
+    assert torch.equal(h.edge_index.cpu(), _t(g["edge_index"]).long())
+    parts = int(g["num_parts"])
+    loader, val, test = h.get_data_training(num_train_clusters=parts)          # METIS runs here
+    assert np.array_equal(np.load("data/indexes/val_indices.npy"), g["val_idx"])
+    assert np.array_equal(np.load("data/indexes/test_indices.npy"), g["test_idx"])
+    train, _, _ = h.get_datasets()                                              # reloads the persisted split
+    assert torch.equal(train.edge_index.cpu(), _t(g["train_edges"]).long())
+    assert torch.equal(val.edge_index.cpu(), h.edge_index.cpu()[:, _t(g["val_idx"])])
+    assert torch.equal(test.edge_index.cpu(), h.edge_index.cpu()[:, _t(g["test_idx"])])
+    sizes = [b.edge_index.shape[1] for b in loader.dataset]
+    assert sizes == g["part_sizes"].tolist()
+    assert torch.equal(torch.cat([b.edge_index for b in loader.dataset], 1).cpu(), _t(g["part_edges"]).long())
+    assert all(b.num_nodes == h.num_users + h.num_movies for b in loader.dataset)
+
+
+def test_to_undirected_kernel_edge_cases():
+    # duplicates in the input, both directions already present, a self loop, non-bipartite ids, explicit num_nodes
+    ei = torch.tensor([[0, 0, 3, 5, 2, 4, 4, 1], [3, 3, 0, 5, 7, 1, 1, 4]], dtype=torch.long)
+    got = dh.to_undirected(ei.to(DEV)).cpu()
+    assert torch.equal(got, pyg.to_undirected(ei))
+    assert torch.equal(dh.to_undirected(ei.to(DEV), num_nodes=12).cpu(), pyg.to_undirected(ei, 12))
+    assert dh.to_undirected(torch.empty(2, 0, dtype=torch.long, device=DEV)).shape == (2, 0)
+    with pytest.raises(_lib.LgcnError):
+        dh.to_undirected(ei.to(DEV), num_nodes=6)                  # id 7 outside [0, 6)
+    # a random multigraph with many duplicates
+    gen = torch.Generator().manual_seed(3)
+    big = torch.randint(0, 3000, (2, 400_000), generator=gen)
+    assert torch.equal(dh.to_undirected(big.to(DEV)).cpu(), pyg.to_undirected(big))
+    # the ML-25M-shaped list: the kernel reproduces the generator's closed form (25 M directed edges)
+    g = synthetic.make_graph("ml25m", seed=0)
+    half = g.edge_index[:, : g.edge_index.shape[1] // 2]
+    assert torch.equal(dh.to_undirected(half.to(DEV)).cpu(), g.edge_index)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -187,3 +243,21 @@ def test_full_rank_eval_metrics_vs_oracle():
     truth = {u: (tm[1, tm[0] == u] - g.num_users) for u in range(g.num_users)}
     r, nd = ref.recall_ndcg_at_k(ids, truth, list(range(g.num_users)), 20)
     assert abs(out["recall"] - r) < 2e-3 and abs(out["ndcg"] - nd) < 2e-3
+
+
+def test_full_rank_eval_user_ranges_sum_to_the_whole():
+    """SURVEY sec. 8e sharded C4: per-range partial sums (what each rank computes) add up to the unsharded metrics."""
+    g = synthetic.make_graph("ml1m", seed=0)
+    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 3)
+    ue, ie = u0.to(DEV), i0.to(DEV)
+    tr, te = g.edges("train").to(DEV), g.edges("test").to(DEV)
+    whole = rec.full_rank_eval(ue, ie, tr, te, g.num_users, k=20)
+    acc = torch.zeros(3, dtype=torch.float64, device=DEV)
+    for lo, hi in rec.user_ranges(g.num_users, 3):
+        part = rec.full_rank_eval(ue, ie, tr, te, g.num_users, k=20, u_begin=lo, u_end=hi)
+        acc += torch.tensor([part["recall"] * part["users"], part["ndcg"] * part["users"], part["users"]],
+                            dtype=torch.float64, device=DEV)
+    assert int(acc[2]) == whole["users"]
+    assert abs(float(acc[0] / acc[2]) - whole["recall"]) < 1e-12 and abs(float(acc[1] / acc[2]) - whole["ndcg"]) < 1e-12
+    one = rec.sharded_full_rank_eval(ue, ie, tr, te, g.num_users, k=20)          # no process group: world 1
+    assert one["recall"] == whole["recall"] and one["user_range"] == (0, g.num_users)

@@ -189,3 +189,36 @@ def test_multi_gpu_c5_10x_graph_step_vs_fp64(tmp_path):
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     _run_full_size(tmp_path, world, "ml25m_x10")
+
+
+def _score_worker(rank, world, port, out_dir):
+    from lgcn_b200.utils import recommend as rec
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dev = torch.device(f"cuda:{rank}")
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}", device_id=dev)
+    g = synthetic.make_graph("ml1m", seed=0)
+    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 3)
+    out = rec.sharded_full_rank_eval(u0.to(dev), i0.to(dev), g.edges("train").to(dev), g.edges("test").to(dev),
+                                     g.num_users, k=20)
+    torch.save(out, os.path.join(out_dir, f"s{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_multi_gpu_sharded_scoring_matches_single_gpu(tmp_path, world):
+    """C4 sharded over user ranges: every rank ends with the single-GPU recall / NDCG."""
+    from lgcn_b200.utils import recommend as rec
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    mp.spawn(_score_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    dev = torch.device("cuda:0")
+    g = synthetic.make_graph("ml1m", seed=0)
+    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 3)
+    want = rec.full_rank_eval(u0.to(dev), i0.to(dev), g.edges("train").to(dev), g.edges("test").to(dev), g.num_users, k=20)
+    res = [torch.load(tmp_path / f"s{r}.pt") for r in range(world)]
+    assert [r["user_range"] for r in res] == rec.user_ranges(g.num_users, world)
+    for r in res:
+        assert r["users"] == want["users"]
+        assert abs(r["recall"] - want["recall"]) < 1e-12 and abs(r["ndcg"] - want["ndcg"]) < 1e-12

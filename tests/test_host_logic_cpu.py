@@ -1,9 +1,13 @@
 """CPU: host-side logic that needs no device -- generator contract, loader semantics, graph cache
 keying, undirected/ exclusion helpers, state_dict layout."""
+import os
+
 import numpy as np
+import pytest
 import torch
 
 import lgcn_b200  # noqa: F401
+from lgcn_b200._lib import LgcnError
 from lgcn_b200.data import dataset_handler as dh
 from lgcn_b200.data import synthetic
 from lgcn_b200.models.light_gcn import GraphCache, LightGCN
@@ -22,7 +26,8 @@ def test_synthetic_graph_contract():
     half = ei.shape[1] // 2
     assert (ei[0, :half] < g.num_users).all() and (ei[1, :half] >= g.num_users).all()
     assert torch.equal(pyg.to_undirected(ei[:, :half]), ei)
-    assert torch.equal(dh.to_undirected(ei[:, :half]), ei)
+    with pytest.raises(LgcnError):                                    # the product's to_undirected is a CUDA kernel
+        dh.to_undirected(ei[:, :half])
     deg = torch.bincount(ei[1], minlength=n)
     assert int(deg.min()) >= 1                                        # every user and item appears
     allidx = torch.sort(torch.cat([g.train_idx, g.val_idx, g.test_idx]))[0]
@@ -115,4 +120,59 @@ def test_graph_handler_split_and_datasets_cpu():
     h2 = dh.GraphDataHandler(g.edge_index, g.num_users, g.num_items, device="cpu")
     a, b, c = h2.get_datasets()
     e = g.edge_index.shape[1]
-    assert a.edge_index.shape[1] == round(0.9 * e) and b.edge_index.shape[1] + c.edge_index.shape[1] == e - round(0.9 * e)
+    assert a.edge_index.shape[1] == int(0.9 * e) and b.edge_index.shape[1] + c.edge_index.shape[1] == e - int(0.9 * e)
+
+
+@pytest.mark.parametrize("n", [20, 31, 1237, 24000])
+def test_shuffle_split_consumes_the_stream_like_sklearn(n):
+    """dataset_handler.py:167-168: the product's restated split == sklearn's train_test_split, index for index, on
+    the same numpy global seed (both calls of the reference: train_size=0.9, then test_size=0.5 of the rest)."""
+    from sklearn.model_selection import train_test_split
+    np.random.seed(77 + n)
+    want_tr, want_vt = train_test_split(np.arange(n), train_size=0.9, shuffle=True)
+    want_va, want_te = train_test_split(want_vt, test_size=0.5, shuffle=True)
+    np.random.seed(77 + n)
+    tr, vt = dh.shuffle_split(n, train_size=0.9)
+    a, b = dh.shuffle_split(len(vt), test_size=0.5)
+    assert np.array_equal(tr, want_tr) and np.array_equal(vt, want_vt)
+    assert np.array_equal(vt[a], want_va) and np.array_equal(vt[b], want_te)
+
+
+def test_handler_split_matches_reference_fixture(tmp_path, monkeypatch):
+    """The reference's own split (np.random.seed(2024), oracle/gen_golden.py::gen_cluster_pipeline) against the
+    product's handler on the same edge list: val / test indices, train edges, and the .npy persist + reload path
+    (dataset_handler.py:160-176, :203-253)."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "cluster_pipeline.npz"))
+    ei = torch.from_numpy(z["edge_index"].astype(np.int64))
+    nu, nm = int(z["num_users"]), int(z["num_movies"])
+    h = dh.GraphDataHandler(ei, nu, nm, device="cpu")
+    np.random.seed(2024)
+    tr, va, te = h.get_datasets()
+    assert np.array_equal(h._split[1], z["val_idx"]) and np.array_equal(h._split[2], z["test_idx"])
+    assert torch.equal(tr.edge_index, torch.from_numpy(z["train_edges"].astype(np.int64)))
+    assert torch.equal(va.edge_index, ei[:, torch.from_numpy(z["val_idx"])])
+    # persist + reload through MovieLensDataHandler._indices (cwd-relative "data/indexes" like the reference)
+    monkeypatch.chdir(tmp_path)
+    m = dh.MovieLensDataHandler.__new__(dh.MovieLensDataHandler)
+    dh.GraphDataHandler.__init__(m, ei, nu, nm, device="cpu")
+    np.random.seed(2024)
+    first = m._indices(0.9)
+    assert os.path.exists("data/indexes/val_indices.npy") and os.path.exists("data/indexes/test_indices.npy")
+    assert np.array_equal(np.load("data/indexes/val_indices.npy"), z["val_idx"])
+    m2 = dh.MovieLensDataHandler.__new__(dh.MovieLensDataHandler)
+    dh.GraphDataHandler.__init__(m2, ei, nu, nm, device="cpu")
+    np.random.seed(5)                                                  # a different stream: the files decide
+    again = m2._indices(0.9)
+    for x, y in zip(first, again):
+        assert np.array_equal(x, y)
+    assert np.array_equal(again[0], np.setdiff1d(np.arange(ei.shape[1]), np.concatenate([z["val_idx"], z["test_idx"]])))
+
+
+def test_user_ranges_for_sharded_scoring():
+    for nu, world in [(162_541, 8), (162_541, 1), (1000, 4), (100, 8), (128, 2)]:
+        r = rec.user_ranges(nu, world)
+        assert len(r) == world and r[0][0] == 0 and r[-1][1] == nu
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:])) and all(lo <= hi for lo, hi in r)
+        assert all(lo % 128 == 0 for lo, _ in r)                     # CTA tiles are not split across ranks
+        sizes = [hi - lo for lo, hi in r]
+        assert max(sizes) - min(s for s in sizes) <= 256 or nu < 128 * world
