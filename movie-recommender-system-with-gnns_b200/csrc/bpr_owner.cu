@@ -189,6 +189,12 @@ struct BprUserOwnOp {
     }
 };
 
+#ifndef LGCN_BPR_USER_MINB
+#define LGCN_BPR_USER_MINB 1          /* tuning knob: resident CTAs per SM the user pass is compiled for */
+#endif
+template <bool kScalars>
+struct MinBlocks<BprUserOwnOp<kScalars>> { static constexpr int value = LGCN_BPR_USER_MINB; };
+
 // ---------------------------------------------------------------------------------------------------
 // item passes: A = sum_t sigma s_t u^_t, B = sum_t sigma s_t c_t over the triplets in which the item plays a
 // role (sigma = +1, c = cos+ as the positive; sigma = -1, c = cos- as the negative);

@@ -241,6 +241,15 @@ bwd_inactive_kernel(const float *__restrict__ G, const uint8_t *__restrict__ act
     }
 }
 
+#ifndef LGCN_SPMM_MINB
+#define LGCN_SPMM_MINB 1              /* tuning knob: resident CTAs per SM the layer kernels are compiled for */
+#endif
+// (the pure gather-sum layers only: the layer-1 kernels with per-edge weights spill at 32 registers)
+template <bool kLast>
+struct MinBlocks<FwdOp<false, kLast>> { static constexpr int value = LGCN_SPMM_MINB; };
+template <bool kLast>
+struct MinBlocks<BwdOp<false, kLast>> { static constexpr int value = LGCN_SPMM_MINB; };
+
 // ---------------------------------------------------------------------------------------
 // host drivers
 // ---------------------------------------------------------------------------------------

@@ -61,8 +61,12 @@ __device__ __forceinline__ void for_each_edge(int begin, int end, int lane, Fetc
 // longest task and the per-task CTA launch cost (measured: 1-warp CTAs were 22 % faster than 8-warp
 // CTAs with static assignment).  sched[0] = next task, sched[1] = finished CTAs; the last CTA to
 // finish resets both, so the pair is zero again when the next launch starts.
+// Minimum resident CTAs per SM the kernel is compiled for (caps its registers); an Op may specialise it.
 template <class Op>
-__global__ void __launch_bounds__(CTA_THREADS)
+struct MinBlocks { static constexpr int value = 1; };
+
+template <class Op>
+__global__ void __launch_bounds__(CTA_THREADS, MinBlocks<Op>::value)
 rowtask_kernel(Op op, const lgcn_task *__restrict__ tasks, int task_begin, int task_end,
                float *__restrict__ partials, int *__restrict__ counters, int *__restrict__ sched) {
     const int lane = threadIdx.x & 31;

@@ -529,3 +529,56 @@ class ShardedTrainer:
                 self._gather(o.y[layer])
         self._gather(o.final)
         return o.final
+
+
+class HostShardPipeline:
+    """Training steps whose edge list arrives from the HOST every step (what the reference's loop does with
+    ``batch.to(device)``, utils/train_test.py:87): the rank's shard (pinned int64 [2,E_r] + its global triplet numbers)
+    is copied on a side stream into one of two device buffers while the previous step is still building its CSR pair
+    and training, so a step costs max(copy, build + train) instead of their sum.  Every step still uploads and
+    rebuilds its own graph; nothing is cached between steps."""
+
+    def __init__(self, trainer: ShardedTrainer, host_edges: torch.Tensor, host_trip: Optional[torch.Tensor] = None):
+        if not host_edges.is_pinned() or (host_trip is not None and not host_trip.is_pinned()):
+            raise ValueError("HostShardPipeline needs pinned host tensors (the copies must be asynchronous)")
+        self.trainer, self.ops = trainer, trainer.ops
+        dev = self.ops.dev
+        self.host_edges, self.host_trip = host_edges, host_trip
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.edges = [torch.empty(host_edges.shape, dtype=host_edges.dtype, device=dev) for _ in range(2)]
+        self.trip = [None if host_trip is None else torch.empty(host_trip.shape, dtype=host_trip.dtype, device=dev)
+                     for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [None, None]                      # recorded on the main stream when a buffer's step has been built
+        self.count, self.pending = 0, None
+        self.bytes_per_step = host_edges.numel() * host_edges.element_size() + (
+            0 if host_trip is None else host_trip.numel() * host_trip.element_size())
+
+    def _copy(self, slot: int) -> None:
+        cs = self.copy_stream
+        if self.free[slot] is not None:
+            cs.wait_event(self.free[slot])
+        else:
+            cs.wait_stream(torch.cuda.current_stream(self.ops.dev))      # the buffers were allocated on the main stream
+        with torch.cuda.stream(cs):
+            self.edges[slot].copy_(self.host_edges, non_blocking=True)
+            if self.host_trip is not None:
+                self.trip[slot].copy_(self.host_trip, non_blocking=True)
+            self.ready[slot].record(cs)
+        self.pending = slot
+
+    def step(self, num_items: Optional[int] = None) -> torch.Tensor:
+        slot = self.count & 1
+        if self.pending != slot:                      # first call (or after a reset): nothing in flight yet
+            self._copy(slot)
+        main = torch.cuda.current_stream(self.ops.dev)
+        main.wait_event(self.ready[slot])
+        self._copy(slot ^ 1)                          # the NEXT step's upload overlaps this step's build + kernels
+        self.trainer.drop_graph()
+        self.ops.load_shard(self.edges[slot], self.trip[slot])
+        ev = torch.cuda.Event()
+        ev.record(main)                               # the CSR pair is built: the edge buffer may be overwritten
+        self.free[slot] = ev
+        loss = self.trainer.step_sampled(num_items, use_graph=False)
+        self.count += 1
+        return loss

@@ -61,6 +61,29 @@ def test_world_one_sharded_step_matches_oracle_and_fused_step(shape, k):
     assert normwise(fin, torch.cat([uf, itf])) < TOL
 
 
+def test_host_shard_pipeline_same_losses_as_device_resident_steps():
+    """sharded.HostShardPipeline (upload of step i+1 overlapped with step i, CSR pair rebuilt every step) against the
+    same steps on a device-resident edge list: identical negatives (same torch CUDA seed) => bit-identical losses."""
+    dev = torch.device("cuda:0")
+    g = synthetic.make_graph("ml100k", seed=0)
+    train = g.edges("train")
+    u0, i0 = synthetic.init_embeddings(g.num_users, g.num_items, 64, 0)
+
+    def run(pipelined):
+        ops = sharded.CudaOps(train.to(dev), g.num_users, g.num_items, 3)
+        tr = sharded.ShardedTrainer(ops, u0.to(dev).clone(), i0.to(dev).clone())
+        torch.manual_seed(11)
+        if not pipelined:
+            return [float(tr.step_sampled(g.num_items, use_graph=False)) for _ in range(5)], tr.gather_weights()
+        pipe = sharded.HostShardPipeline(tr, train.clone().pin_memory(), None)
+        return [float(pipe.step(g.num_items)) for _ in range(5)], tr.gather_weights()
+    a, wa = run(False)
+    b, wb = run(True)
+    assert a == b and torch.equal(wa[0], wb[0]) and torch.equal(wa[1], wb[1])
+    with pytest.raises(ValueError):
+        sharded.HostShardPipeline(None, train, None)                 # pageable memory: the copy could not overlap
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

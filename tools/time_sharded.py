@@ -14,7 +14,7 @@ import torch.distributed as dist
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import lgcn_b200  # noqa: E402,F401
-from lgcn_b200 import sharded  # noqa: E402
+from lgcn_b200 import _lib, sharded  # noqa: E402
 from lgcn_b200.data import synthetic  # noqa: E402
 
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
@@ -24,7 +24,16 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 shape = os.environ.get("LGCN_BENCH_SHAPE", "ml25m")
 k = synthetic.SHAPES[shape][3]
-nu, ni, train, _ = synthetic.shared_train_edges(shape, local, dist.barrier if world > 1 else (lambda: None))
+cache = os.environ.get("LGCN_EDGE_CACHE")             # A/B runs of library variants: generate the graph once
+if cache and world == 1 and os.path.exists(cache):
+    import numpy as np
+    nu, ni = synthetic.SHAPES[shape][0], synthetic.SHAPES[shape][1]
+    train = torch.from_numpy(np.load(cache)).to(torch.int64)
+else:
+    nu, ni, train, _ = synthetic.shared_train_edges(shape, local, dist.barrier if world > 1 else (lambda: None))
+    if cache and world == 1:
+        import numpy as np
+        np.save(cache, train.numpy().astype(np.int32))
 
 
 class g:                                   # noqa: N801  (the few graph facts used below)
@@ -36,7 +45,7 @@ u0, i0 = synthetic.init_embeddings(nu, ni, 64, 0)
 t = sharded.ShardedTrainer(ops, u0.to(dev), i0.to(dev), sharded.Comm())
 torch.manual_seed(0)
 neg = torch.randint(0, g.num_items, (ops.num_triplets,), device=dev)
-t.step(neg)
+first_loss = float(t.step(neg))
 
 
 def timed(fn, iters=20, warm=3):
@@ -86,6 +95,7 @@ if rank == 0:
     print(f"world {world} shape {shape} p2p {ops.p2p} multicast {ops.multicast} graph "
           f"{'yes' if getattr(t, '_graph', None) is not None else 'no: ' + str(getattr(t, '_graph_error', ''))}",
           {key: round(v, 1) for key, v in res.items()})
+    print("lib", os.path.basename(_lib.LIB_PATH), "first step loss", repr(first_loss))
     print("shard edges", ops.g.num_edges, "of", ops.E, "local tasks in/out", ops.local.n_in_tasks, ops.local.n_out_tasks)
 if world > 1:
     dist.barrier()
