@@ -189,11 +189,13 @@ struct BprUserOwnOp {
     }
 };
 
-#ifndef LGCN_BPR_USER_MINB
-#define LGCN_BPR_USER_MINB 1          /* tuning knob: resident CTAs per SM the user pass is compiled for */
+// Resident warps per SM the user pass is compiled for (32 = a 64-register cap instead of 110 registers / 16 warps):
+// the whole BPR stage 1938 -> 1705 us at ML-25M shape (profiles/r2b_variants.txt), bit-identical results.
+#ifndef LGCN_BPR_USER_MINWARPS
+#define LGCN_BPR_USER_MINWARPS 32
 #endif
 template <bool kScalars>
-struct MinBlocks<BprUserOwnOp<kScalars>> { static constexpr int value = LGCN_BPR_USER_MINB; };
+struct MinBlocks<BprUserOwnOp<kScalars>> { static constexpr int value = LGCN_BPR_USER_MINWARPS / WARPS_PER_CTA; };
 
 // ---------------------------------------------------------------------------------------------------
 // item passes: A = sum_t sigma s_t u^_t, B = sum_t sigma s_t c_t over the triplets in which the item plays a
@@ -277,6 +279,17 @@ struct ItemGather {
     }
 };
 
+#ifndef LGCN_BPR_ITEM_MINWARPS
+#define LGCN_BPR_ITEM_MINWARPS 64     /* resident warps per SM the item passes are compiled for (0 = no hint): 64 = a 32-register
+                                         cap, BPR stage 1636 -> 1590 us (profiles/r2c_variants.txt);
+                                         (single-GPU form that reads the per-triplet scalars; the recomputing form of the
+                                         sharded step needs its 64 registers) */
+#endif
+template <bool kScalars>
+struct BprItemOwnOp;
+template <bool kScalars>
+struct MinBlocks<BprItemOwnOp<kScalars>> { static constexpr int value = kScalars ? LGCN_BPR_ITEM_MINWARPS / WARPS_PER_CTA : 0; };
+
 template <bool kScalars>
 struct BprItemOwnOp {
     static constexpr bool kExtras = false;
@@ -312,7 +325,7 @@ struct BprItemOwnOp {
 // One warp per owned item row [ib,ie) (dynamic): the negative-role gradient from the row's bucket.  WRITES G[row]
 // (zero for an empty bucket), so G needs no clearing; rows without in-edges keep zG = 0 (dis = 0).
 template <bool kScalars>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, kScalars ? LGCN_BPR_ITEM_MINWARPS / WARPS_PER_CTA : 0)
 bpr_neg_kernel(ItemGather<kScalars, true> gather, const float *__restrict__ rnorm,
                const int32_t *__restrict__ bucket_ptr, int ib, int ie, float invP, float *__restrict__ G,
                int *__restrict__ sched) {

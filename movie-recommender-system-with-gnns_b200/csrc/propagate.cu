@@ -241,14 +241,18 @@ bwd_inactive_kernel(const float *__restrict__ G, const uint8_t *__restrict__ act
     }
 }
 
-#ifndef LGCN_SPMM_MINB
-#define LGCN_SPMM_MINB 1              /* tuning knob: resident CTAs per SM the layer kernels are compiled for */
+// Resident warps per SM the pure gather-sum layer kernels are compiled for (a register cap + a scheduling hint for
+// ptxas): 48 warps = 6 CTAs = at most 40 registers.  Measured on B200 at ML-25M shape, bit-identical results
+// (profiles/r2b_variants.txt, r2c_variants.txt): no hint (40 registers) fwd 442 / bwd 470-500 us per layer;
+// hint 64 warps (32 registers) 383 / 376 us; hint 48 warps 376 / 367 us.  (The layer-1 kernels with per-edge weights
+// spill under a cap and keep ptxas' own choice.)
+#ifndef LGCN_SPMM_MINWARPS
+#define LGCN_SPMM_MINWARPS 48
 #endif
-// (the pure gather-sum layers only: the layer-1 kernels with per-edge weights spill at 32 registers)
 template <bool kLast>
-struct MinBlocks<FwdOp<false, kLast>> { static constexpr int value = LGCN_SPMM_MINB; };
+struct MinBlocks<FwdOp<false, kLast>> { static constexpr int value = LGCN_SPMM_MINWARPS / WARPS_PER_CTA; };
 template <bool kLast>
-struct MinBlocks<BwdOp<false, kLast>> { static constexpr int value = LGCN_SPMM_MINB; };
+struct MinBlocks<BwdOp<false, kLast>> { static constexpr int value = LGCN_SPMM_MINWARPS / WARPS_PER_CTA; };
 
 // ---------------------------------------------------------------------------------------
 // host drivers

@@ -63,7 +63,7 @@ __device__ __forceinline__ void for_each_edge(int begin, int end, int lane, Fetc
 // finish resets both, so the pair is zero again when the next launch starts.
 // Minimum resident CTAs per SM the kernel is compiled for (caps its registers); an Op may specialise it.
 template <class Op>
-struct MinBlocks { static constexpr int value = 1; };
+struct MinBlocks { static constexpr int value = 0; };   // 0 = no hint (ptxas picks the register count itself)
 
 template <class Op>
 __global__ void __launch_bounds__(CTA_THREADS, MinBlocks<Op>::value)

@@ -63,7 +63,8 @@ def test_world_one_sharded_step_matches_oracle_and_fused_step(shape, k):
 
 def test_host_shard_pipeline_same_losses_as_device_resident_steps():
     """sharded.HostShardPipeline (upload of step i+1 overlapped with step i, CSR pair rebuilt every step) against the
-    same steps on a device-resident edge list: identical negatives (same torch CUDA seed) => bit-identical losses."""
+    same steps on a device-resident edge list with identical negatives (same torch CUDA seed).  The loss and the clip norm
+    are double sums accumulated with one atomic per CTA, so two runs may differ in the last float bit -- nothing more."""
     dev = torch.device("cuda:0")
     g = synthetic.make_graph("ml100k", seed=0)
     train = g.edges("train")
@@ -79,7 +80,8 @@ def test_host_shard_pipeline_same_losses_as_device_resident_steps():
         return [float(pipe.step(g.num_items)) for _ in range(5)], tr.gather_weights()
     a, wa = run(False)
     b, wb = run(True)
-    assert a == b and torch.equal(wa[0], wb[0]) and torch.equal(wa[1], wb[1])
+    assert max(abs(x - y) / abs(x) for x, y in zip(a, b)) < 1e-6
+    assert max_abs(wa[0], wb[0]) < 1e-7 and max_abs(wa[1], wb[1]) < 1e-7
     with pytest.raises(ValueError):
         sharded.HostShardPipeline(None, train, None)                 # pageable memory: the copy could not overlap
 
