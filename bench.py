@@ -243,8 +243,9 @@ def run_full_graph(args):
     if world > 1 and not dist.is_initialized():
         # NCCL logs to stdout (INIT lines name the communicator's nranks): for the rest of the run fd 1 is stderr, and
         # the JSON line goes out through the saved descriptor (emit_line), so stdout carries nothing else
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        if os.environ.get("NCCL_DEBUG", "WARN").upper() in ("WARN", "VERSION"):     # the INIT lines are the evidence of nranks / NVLS
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         sys.stdout.flush()
         global _REAL_STDOUT
         _REAL_STDOUT = os.dup(1)
