@@ -218,6 +218,7 @@ def staged_step(trainer, neg, acc):
         a.record(); fn(); z.record()
         acc.setdefault(name, []).append((a, z))
     timed("step_begin+prescale", lambda: (o.step_begin(), o.prescale()))
+    timed("bpr_buckets", lambda: o.bpr_buckets(neg))               # overlaps the y_0 exchange (see ShardedTrainer.step)
     timed("exchange", lambda: trainer._gather(o.y[0]))
     for layer in range(1, k + 1):
         timed("spmm_fwd_layer", lambda layer=layer: o.fwd_layer(layer))

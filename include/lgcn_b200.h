@@ -313,6 +313,17 @@ int lgcn_bpr_owner(const lgcn_graph *g, const float *final_hat, const float *rno
                    const lgcn_bpr_owner_ws *ws, int user_task_begin, int user_task_end, int item_task_begin,
                    int item_task_end, int64_t item_begin, int64_t item_end, const lgcn_peers *peers, void *stream);
 
+/* The two halves of lgcn_bpr_owner, for callers that overlap them with an exchange: lgcn_bpr_buckets groups this
+ * step's negatives by item for items [item_begin,item_end) (needs only `neg`: it can run while the forward tables are
+ * still in flight); lgcn_bpr_owner_passes runs the user / negative / positive passes on buckets built that way.
+ * lgcn_bpr_owner == lgcn_bpr_buckets followed by lgcn_bpr_owner_passes. */
+int lgcn_bpr_buckets(const int64_t *neg, int64_t num_triplets, int64_t item_begin, int64_t item_end,
+                     int32_t *neg_count, const lgcn_bpr_owner_ws *ws, void *stream);
+int lgcn_bpr_owner_passes(const lgcn_graph *g, const float *final_hat, const float *rnorm, const int64_t *neg,
+                          int64_t num_triplets, float *G, float *zG, int32_t *neg_count, double *accum,
+                          const lgcn_bpr_owner_ws *ws, int user_task_begin, int user_task_end, int item_task_begin,
+                          int item_task_end, int64_t item_begin, int64_t item_end, const lgcn_peers *peers, void *stream);
+
 /* trip_user[t] / trip_pos[t] for the triplets of the user rows covered by out-tasks [user_task_begin,user_task_end),
  * stored into every rank's copy of the two tables (symmetric memory when peers != NULL).  One-off per edge list. */
 int lgcn_triplet_index(const lgcn_graph *g, int user_task_begin, int user_task_end, int32_t *trip_user,

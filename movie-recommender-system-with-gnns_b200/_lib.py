@@ -32,7 +32,7 @@ EXPORTS = [
     "lgcn_train_steps_workspace_bytes", "lgcn_train_steps_sparse", "lgcn_probe_gather",
     "lgcn_score_topk_workspace_bytes", "lgcn_upload_lists",
     "lgcn_bpr_owner", "lgcn_fwd_layer_ex", "lgcn_triplet_index", "lgcn_graph_remap_triplets", "lgcn_peer_allreduce4",
-    "lgcn_to_undirected_workspace_bytes", "lgcn_to_undirected",
+    "lgcn_to_undirected_workspace_bytes", "lgcn_to_undirected", "lgcn_bpr_buckets", "lgcn_bpr_owner_passes",
 ]
 
 
@@ -152,6 +152,8 @@ def lib():
     L.lgcn_bpr_owner.argtypes = [POINTER(CGraph), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                  c_void_p, POINTER(CBprOwnerWs), c_int, c_int, c_int, c_int, c_int64, c_int64,
                                  POINTER(CPeers), c_void_p]
+    L.lgcn_bpr_owner_passes.argtypes = L.lgcn_bpr_owner.argtypes
+    L.lgcn_bpr_buckets.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_void_p, POINTER(CBprOwnerWs), c_void_p]
     L.lgcn_triplet_index.argtypes = [POINTER(CGraph), c_int, c_int, c_void_p, c_void_p, POINTER(CPeers), c_void_p]
     L.lgcn_graph_remap_triplets.argtypes = [POINTER(CGraph), c_void_p, c_void_p]
     L.lgcn_train_step_sparse.argtypes = L.lgcn_train_step.argtypes

@@ -568,11 +568,39 @@ extern "C" int lgcn_graph_remap_triplets(lgcn_graph *g, const int32_t *trip_glob
     return LGCN_OK;
 }
 
-extern "C" int lgcn_bpr_owner(const lgcn_graph *g, const float *final_hat, const float *rnorm, const int64_t *neg,
-                              int64_t num_triplets, float *G, float *zG, int32_t *neg_count, double *accum,
-                              const lgcn_bpr_owner_ws *ws, int user_task_begin, int user_task_end,
-                              int item_task_begin, int item_task_end, int64_t item_begin, int64_t item_end,
-                              const lgcn_peers *peers, void *stream) {
+extern "C" int lgcn_bpr_buckets(const int64_t *neg, int64_t num_triplets, int64_t item_begin, int64_t item_end,
+                                int32_t *neg_count, const lgcn_bpr_owner_ws *ws, void *stream) {
+    using namespace lgcn;
+    cudaStream_t st = (cudaStream_t)stream;
+    LGCN_REQUIRE(neg && neg_count && ws && ws->bucket_ptr && ws->bucket_cursor && ws->bucket, LGCN_E_INVALID,
+                 "bpr_buckets: null argument");
+    LGCN_REQUIRE(num_triplets > 0 && num_triplets < ((int64_t)1 << 31), LGCN_E_INVALID, "bpr_buckets: %lld triplets",
+                 (long long)num_triplets);
+    LGCN_REQUIRE(item_begin >= 0 && item_begin <= item_end && item_end < ((int64_t)1 << 31), LGCN_E_INVALID,
+                 "bpr_buckets: item range [%lld,%lld)", (long long)item_begin, (long long)item_end);
+    LGCN_REQUIRE(ws->bucket_cap >= num_triplets, LGCN_E_WORKSPACE, "bpr_buckets: bucket array holds %lld < %lld entries",
+                 (long long)ws->bucket_cap, (long long)num_triplets);
+    const int ib = (int)item_begin, ie = (int)item_end, ni = ie - ib;
+    if (ni <= 0) return LGCN_OK;
+    // buckets of this step's negatives for the owned items (also the histogram the regulariser needs)
+    LGCN_CUDA(cudaMemsetAsync(neg_count + ib, 0, sizeof(int32_t) * (size_t)ni, st));
+    const int grid = grid_for(num_triplets, 256, 148 * 8);
+    neg_hist_kernel<<<grid, 256, 0, st>>>(neg, num_triplets, ib, ie, neg_count, nullptr);
+    LGCN_LAUNCH_CHECK();
+    bucket_scan_kernel<<<1, 1024, 0, st>>>(neg_count, ib, ni, ws->bucket_ptr, ws->bucket_cursor);
+    LGCN_LAUNCH_CHECK();
+    bucket_fill_kernel<<<grid, 256, 0, st>>>(neg, num_triplets, ib, ie, ws->bucket_cursor, ws->bucket, ws->bucket_cap);
+    LGCN_LAUNCH_CHECK();
+    bucket_sort_kernel<<<grid_for(ni, 4, 148 * 16), 128, 0, st>>>(ws->bucket_ptr, ni, ws->bucket);
+    LGCN_LAUNCH_CHECK();
+    return LGCN_OK;
+}
+
+static int bpr_owner_impl(bool build_buckets, const lgcn_graph *g, const float *final_hat, const float *rnorm,
+                          const int64_t *neg, int64_t num_triplets, float *G, float *zG, int32_t *neg_count, double *accum,
+                          const lgcn_bpr_owner_ws *ws, int user_task_begin, int user_task_end, int item_task_begin,
+                          int item_task_end, int64_t item_begin, int64_t item_end, const lgcn_peers *peers, void *stream) {
+
     using namespace lgcn;
     cudaStream_t st = (cudaStream_t)stream;
     LGCN_REQUIRE(g && final_hat && rnorm && neg && G && zG && neg_count && accum && ws, LGCN_E_INVALID,
@@ -596,18 +624,9 @@ extern "C" int lgcn_bpr_owner(const lgcn_graph *g, const float *final_hat, const
     float2 *s_cp = reinterpret_cast<float2 *>(ws->scalars);
     float2 *s_cn = s_cp ? s_cp + num_triplets : nullptr;
 
-    // buckets of this step's negatives for the owned items (also the histogram the regulariser needs)
-    if (ni > 0) {
-        LGCN_CUDA(cudaMemsetAsync(neg_count + ib, 0, sizeof(int32_t) * (size_t)ni, st));
-        const int grid = grid_for(num_triplets, 256, 148 * 8);
-        neg_hist_kernel<<<grid, 256, 0, st>>>(neg, num_triplets, ib, ie, neg_count, nullptr);
-        LGCN_LAUNCH_CHECK();
-        bucket_scan_kernel<<<1, 1024, 0, st>>>(neg_count, ib, ni, ws->bucket_ptr, ws->bucket_cursor);
-        LGCN_LAUNCH_CHECK();
-        bucket_fill_kernel<<<grid, 256, 0, st>>>(neg, num_triplets, ib, ie, ws->bucket_cursor, ws->bucket, ws->bucket_cap);
-        LGCN_LAUNCH_CHECK();
-        bucket_sort_kernel<<<grid_for(ni, 4, 148 * 16), 128, 0, st>>>(ws->bucket_ptr, ni, ws->bucket);
-        LGCN_LAUNCH_CHECK();
+    if (build_buckets && ni > 0) {
+        const int rc = lgcn_bpr_buckets(neg, num_triplets, item_begin, item_end, neg_count, ws, stream);
+        if (rc != LGCN_OK) return rc;
     }
     // user rows
     auto users = [&](auto op) {
@@ -649,4 +668,22 @@ extern "C" int lgcn_bpr_owner(const lgcn_graph *g, const float *final_hat, const
                                                                      nullptr, final_hat, g->num_users},
                                             rnorm, g->dis, invP, G, zG, P}));
     return LGCN_OK;
+}
+
+extern "C" int lgcn_bpr_owner(const lgcn_graph *g, const float *final_hat, const float *rnorm, const int64_t *neg,
+                              int64_t num_triplets, float *G, float *zG, int32_t *neg_count, double *accum,
+                              const lgcn_bpr_owner_ws *ws, int user_task_begin, int user_task_end,
+                              int item_task_begin, int item_task_end, int64_t item_begin, int64_t item_end,
+                              const lgcn_peers *peers, void *stream) {
+    return bpr_owner_impl(true, g, final_hat, rnorm, neg, num_triplets, G, zG, neg_count, accum, ws, user_task_begin,
+                          user_task_end, item_task_begin, item_task_end, item_begin, item_end, peers, stream);
+}
+
+extern "C" int lgcn_bpr_owner_passes(const lgcn_graph *g, const float *final_hat, const float *rnorm, const int64_t *neg,
+                                     int64_t num_triplets, float *G, float *zG, int32_t *neg_count, double *accum,
+                                     const lgcn_bpr_owner_ws *ws, int user_task_begin, int user_task_end,
+                                     int item_task_begin, int item_task_end, int64_t item_begin, int64_t item_end,
+                                     const lgcn_peers *peers, void *stream) {
+    return bpr_owner_impl(false, g, final_hat, rnorm, neg, num_triplets, G, zG, neg_count, accum, ws, user_task_begin,
+                          user_task_end, item_task_begin, item_task_end, item_begin, item_end, peers, stream);
 }

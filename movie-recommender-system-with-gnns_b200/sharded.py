@@ -378,10 +378,21 @@ class CudaOps:
                 self._fwd_call(self.g.ref, k, 0, 0, rb, re, normalized)
         self._fwd_call(byref(self.local), k, 0, self.local.n_in_tasks, 0, 0, normalized)
 
+    def bpr_buckets(self, neg):
+        """This step's negatives grouped by owned item.  Needs only ``neg``: the trainer runs it between the launch that
+        produces y_0 and the barrier that waits for the peers' rows, so it hides behind that exchange."""
+        (_, _), (ib, ie) = self.segs
+        self._lib.check(self.L.lgcn_bpr_buckets(neg.data_ptr(), self.P, ib - self.nu, ie - self.nu,
+                                                self.neg_count.data_ptr(), byref(self.bpr_ws), self._s()))
+        self._buckets_for = neg.data_ptr()
+
     def bpr(self, neg):
         (_, _), (ib, ie) = self.segs
         c = self.local_bpr
-        self._lib.check(self.L.lgcn_bpr_owner(
+        prebuilt = getattr(self, "_buckets_for", None) == neg.data_ptr()
+        self._buckets_for = None
+        fn = self.L.lgcn_bpr_owner_passes if prebuilt else self.L.lgcn_bpr_owner
+        self._lib.check(fn(
             byref(c), self.final.data_ptr(), self.rnorm.data_ptr(), neg.data_ptr(), self.P, self.G.data_ptr(),
             self.zg.data_ptr(), self.neg_count.data_ptr(), self.accum.data_ptr(), byref(self.bpr_ws),
             0, c.n_out_tasks, 0, c.n_in_tasks, ib - self.nu, ie - self.nu, self._p(), self._s()))
@@ -453,13 +464,23 @@ class ShardedTrainer:
             self.comm.allreduce(o.trip_user)
             self.comm.allreduce(o.trip_pos)
 
-    def step(self, neg: torch.Tensor) -> torch.Tensor:
-        """One step; ``neg`` is the FULL [P] negative vector (identical on every rank).  Returns the loss as a device
-        tensor (same on every rank)."""
+    def step(self, neg: Optional[torch.Tensor] = None, num_items: Optional[int] = None) -> torch.Tensor:
+        """One step; ``neg`` is the FULL [P] negative vector (identical on every rank), or None: sampled here the way the
+        reference does (uniform ``randint`` per triplet, utils/helpers.py:79-80; all ranks must share the torch CUDA RNG
+        state).  Returns the loss as a device tensor (same on every rank).
+
+        Work that does not depend on the exchanged tables -- sampling, grouping the negatives by item -- is issued
+        between the kernel that produces y_0 and the barrier that waits for the peers' rows: it runs while the NVLink
+        transfers of the first exchange are in flight."""
         o, k = self.ops, self.k
         p2p = getattr(o, "p2p", False)
         o.step_begin()
         o.prescale()
+        if neg is None:
+            ni = self.plan.num_items if num_items is None else num_items
+            neg = torch.randint(0, ni, (o.num_triplets,), device=self.user_w.device)
+        if hasattr(o, "bpr_buckets"):
+            o.bpr_buckets(neg)
         self._gather(o.y[0])
         for layer in range(1, k + 1):
             o.fwd_layer(layer)
@@ -488,21 +509,21 @@ class ShardedTrainer:
         p, dev = self.ops.num_triplets, self.user_w.device
         self._calls = getattr(self, "_calls", 0) + 1
         if not use_graph or not self.user_w.is_cuda or getattr(self, "_graph_failed", False):
-            return self.step(torch.randint(0, ni, (p,), device=dev))
+            return self.step(None, ni)
         if getattr(self, "_graph", None) is None:
             if self._calls <= 3:                       # eager warm-up (allocator, lazy module loading)
-                return self.step(torch.randint(0, ni, (p,), device=dev))
+                return self.step(None, ni)
             try:
                 torch.cuda.synchronize(dev)
                 self.comm.barrier()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._graph_loss = self.step(torch.randint(0, ni, (p,), device=dev))
+                    self._graph_loss = self.step(None, ni)
                 self._graph = g
             except Exception as exc:                   # capture not supported for some op: stay eager
                 self._graph_failed, self._graph_error = True, f"{type(exc).__name__}: {exc}"
                 torch.cuda.synchronize(dev)
-                return self.step(torch.randint(0, ni, (p,), device=dev))
+                return self.step(None, ni)
         self._graph.replay()
         return self._graph_loss
 
