@@ -622,7 +622,10 @@ def block_eval_c4(nu, ni, train_dev, test_dev, steps):
             "roofline": {"kernel": "score_topk_tc_kernel (tcgen05.mma kind::tf32, 3-term hi/lo split)", "bound": "tensor",
                          "achieved": 3 * flop / (ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": 3 * flop / (ms * 1e-3) / 1e12 / tf32_peak,
-                         "peak_source": "half the measured dense bf16 peak (MEASURED_PEAKS.json)", "traffic": None},
+                         "peak_source": "half the measured dense bf16 peak (MEASURED_PEAKS.json)", "traffic": None,
+                         "tensor_pipe_cycles_active_pct_ncu": (json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json")))
+                                                               .get("score_topk_tc_one_wave_r2", {}).get("tensor_pipe_cycles_active_pct")
+                                                               if os.path.exists(os.path.join(REPO, "profiles", "roofline_traffic.json")) else None)},
             "math": "tcgen05.mma kind::tf32, 3-term hi/lo split (fp32-level accuracy), fp32 accumulate in TMEM",
             "ffma_kernel_ms": ms_ffma, "recall@20": m["recall"], "ndcg@20": m["ndcg"],
             "users_with_test_items": m["users"], "note": "random-init embeddings: recall/NDCG are chance level"}
