@@ -532,6 +532,23 @@ def block_cluster_gcn_c2(nu, ni, train, k, dev, steps, warmup, with_cpu):
                    "note": "train() over HOST (pinned) batches: every epoch uploads all edge lists, rebuilds every "
                            "batch's normalisation / CSR (one batched K0b call) and reads the losses back"},
            "roofline": roof, "final_epoch_loss": last, "gpu_launches_per_epoch": 2}
+    try:                                                            # f4: the GPU partitioner next to METIS (set-up stage, untimed above)
+        from lgcn_b200.data import partition_gpu as pg
+        tr_dev = train.to(dev)
+        pg.partition(tr_dev, n, NUM_PARTS, nu)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, st = pg.partition(tr_dev, n, NUM_PARTS, nu)
+        torch.cuda.synchronize()
+        blk["gpu_partitioner"] = {"ms": (time.perf_counter() - t0) * 1e3, "intra_edge_share": st["intra_edge_share"],
+                                  "metis_intra_edge_share": edges_per_epoch / train.shape[1], "max_part": st["max_part"],
+                                  "starts": st["starts"],
+                                  "note": "balanced label propagation on the device (data/partition_gpu.py), wall clock incl. its "
+                                          "host syncs; METIS on the host takes ~75 s for this graph; the epoch above trains on the "
+                                          "METIS parts (the reference's partitions)"}
+        del tr_dev
+    except Exception as exc:
+        blk["gpu_partitioner"] = {"error": repr(exc)[:300]}
     if with_cpu:
         batches = [b for b in cluster_batches_cpu(train, cluster, n) if int((b[0] < nu).sum()) > 0]
         blk["cpu_baseline"] = cpu_cluster_epoch(nu, ni, batches, k)

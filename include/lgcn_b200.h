@@ -419,6 +419,15 @@ int lgcn_cluster_extract(const int64_t *edge_index, int64_t num_edges, int64_t n
                          const int64_t *cluster, int64_t num_parts, int64_t *out_edges,
                          int64_t *part_ptr, void *workspace, size_t workspace_bytes, void *stream);
 
+/* GPU partitioner (alternative to the host METIS call above; partitions differ from METIS, so this is a set-up-time /
+ * quality trade, not a parity item -- SURVEY sec. 8f rank 4).  One voting pass of balanced label propagation over rows
+ * [row_begin,row_end) of a CSR by source (ptr [N+1], nbr [E], device int32): want[v] = the part label carried by most
+ * out-neighbours of v (ties: the smallest label; v's own label if it has no out-neighbour), best[v] = that count,
+ * own[v] = out-neighbours carrying v's current label.  num_parts <= 4096.  Deterministic integer work; the
+ * capacity-constrained acceptance of the moves is host orchestration (lgcn_b200/data/partition_gpu.py). */
+int lgcn_label_vote(const int32_t *ptr, const int32_t *nbr, const int32_t *labels, int64_t row_begin, int64_t row_end,
+                    int num_parts, int32_t *want, int32_t *best, int32_t *own, void *stream);
+
 /* to_undirected (PyG 2.4.0 utils/undirected.py:to_undirected + coalesce, called at
  * data/dataset_handler.py:141): both directions of every edge of edge_index [2,E] int64 (device), sorted by
  * (row, col), duplicates dropped.  out_edges: device int64, 4*E cells; on return cells [0,count) hold the rows

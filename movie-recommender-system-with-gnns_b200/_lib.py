@@ -33,6 +33,7 @@ EXPORTS = [
     "lgcn_score_topk_workspace_bytes", "lgcn_upload_lists",
     "lgcn_bpr_owner", "lgcn_fwd_layer_ex", "lgcn_triplet_index", "lgcn_graph_remap_triplets", "lgcn_peer_allreduce4",
     "lgcn_to_undirected_workspace_bytes", "lgcn_to_undirected", "lgcn_bpr_buckets", "lgcn_bpr_owner_passes",
+    "lgcn_label_vote",
 ]
 
 
@@ -125,6 +126,7 @@ def lib():
     L.lgcn_cluster_extract_workspace_bytes.restype = c_size_t
     L.lgcn_cluster_extract.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                        c_size_t, c_void_p]
+    L.lgcn_label_vote.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.lgcn_to_undirected_workspace_bytes.argtypes = [c_int64]
     L.lgcn_to_undirected_workspace_bytes.restype = c_size_t
     L.lgcn_to_undirected.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]

@@ -21,7 +21,7 @@ CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 METIS_A = os.path.join(CUDA_HOME, "targets", "x86_64-linux", "lib", "libmetis_static.a")
 
-CU_SOURCES = ["api.cu", "graph_build.cu", "propagate.cu", "bpr.cu", "adam.cu", "cluster.cu", "score_topk.cu", "rows.cu", "sparse_step.cu", "score_topk_tc.cu", "graph_build_batched.cu", "epoch_kernel.cu", "probe.cu", "bpr_owner.cu"]
+CU_SOURCES = ["api.cu", "graph_build.cu", "propagate.cu", "bpr.cu", "adam.cu", "cluster.cu", "score_topk.cu", "rows.cu", "sparse_step.cu", "score_topk_tc.cu", "graph_build_batched.cu", "epoch_kernel.cu", "probe.cu", "bpr_owner.cu", "partition_gpu.cu"]
 C_SOURCES = ["partition_metis.c"]
 HEADERS = ["common.cuh", "rowtask.cuh", "adam.cuh"]
 

@@ -146,10 +146,22 @@ class ClusterData:
     (dataset_handler.py:273-282), all parts at once.  Iterating yields ``Data`` with GLOBAL ids,
     ``num_nodes = N`` and ``n_id = arange(N)``."""
 
-    def __init__(self, data: Data, num_parts: int, cluster: Optional[torch.Tensor] = None):
+    def __init__(self, data: Data, num_parts: int, cluster: Optional[torch.Tensor] = None,
+                 partitioner: str = "metis", num_users: Optional[int] = None):
+        """``cluster``: a ready partition vector; else ``partitioner`` computes one: "metis" = the host call PyG makes
+        (the reference's partitions), "gpu" = balanced label propagation on the device (data/partition_gpu.py: other
+        partitions, no host stage; ``num_users`` tells it the bipartite sides)."""
         n = data.num_nodes
         self.num_parts = num_parts
-        self.cluster = metis_partition(data.edge_index, n, num_parts) if cluster is None else cluster
+        if cluster is not None:
+            self.cluster = cluster
+        elif partitioner == "metis":
+            self.cluster = metis_partition(data.edge_index, n, num_parts)
+        elif partitioner == "gpu":
+            from .partition_gpu import gpu_partition
+            self.cluster = gpu_partition(data.edge_index, n, num_parts, num_users)
+        else:
+            raise ValueError(f"unknown partitioner {partitioner!r} (metis | gpu)")
         edges, part_ptr = cluster_extract(data.edge_index, n, self.cluster, num_parts)
         self.part_ptr = part_ptr.cpu()
         n_id = torch.arange(n, device=edges.device)
@@ -204,10 +216,11 @@ class GraphDataHandler:
             out.append(d)
         return tuple(out)
 
-    def get_data_training(self, num_train_clusters: int = 100, cluster: Optional[torch.Tensor] = None
-                          ) -> Tuple[ClusterLoader, Data, Data]:
+    def get_data_training(self, num_train_clusters: int = 100, cluster: Optional[torch.Tensor] = None,
+                          partitioner: str = "metis") -> Tuple[ClusterLoader, Data, Data]:
         train, val, test = self.get_datasets()
-        cd = ClusterData(train, num_parts=num_train_clusters, cluster=cluster)
+        cd = ClusterData(train, num_parts=num_train_clusters, cluster=cluster, partitioner=partitioner,
+                         num_users=self.num_users)
         return ClusterLoader(cd.parts, shuffle=True), val, test
 
     def get_num_users_items(self) -> Tuple[int, int]:

@@ -137,6 +137,34 @@ def test_to_undirected_kernel_edge_cases():
     assert torch.equal(dh.to_undirected(half.to(DEV)).cpu(), g.edge_index)
 
 
+@pytest.mark.parametrize("shape,parts", [("ml100k", 16), ("ml1m", 100)])
+def test_gpu_partitioner_vote_kernel_and_partition_match_torch_restatement(shape, parts):
+    """f4: lgcn_label_vote against tests/partition_ref.py row by row, and the whole partition (device orchestration +
+    kernel) against the same orchestration on the CPU with the torch vote -- bit-exact; then ClusterData with it."""
+    import math
+    from partition_ref import torch_vote
+    from lgcn_b200.data import partition_gpu as pg
+    g = synthetic.make_graph(shape, seed=0)
+    tr, n = g.edges("train"), g.num_nodes
+    ptr, nbr = pg.csr_by_source(tr.to(DEV), n)
+    lab0 = pg.hash_labels(n, parts, DEV)
+    for b, e in ((0, n), (g.num_users, n), (0, g.num_users)):
+        got = pg.cuda_vote(ptr, nbr, lab0, b, e, parts)
+        want = torch_vote(ptr.cpu(), nbr.cpu(), lab0.cpu(), b, e, parts)
+        for a, w in zip(got, want):
+            assert torch.equal(a.cpu(), w)
+    lab, st = pg.partition(tr.to(DEV), n, parts, g.num_users)
+    ref_lab, ref_st = pg.partition(tr, n, parts, g.num_users, vote=torch_vote)
+    assert torch.equal(lab.cpu(), ref_lab) and st == ref_st
+    assert st["max_part"] <= math.ceil(n / parts * 1.03)
+    cd = dh.ClusterData(dh.Data(edge_index=tr.to(DEV), num_nodes=n), parts, partitioner="gpu", num_users=g.num_users)
+    assert torch.equal(cd.cluster.cpu(), ref_lab)
+    kept = sum(d.edge_index.shape[1] for d in cd)
+    assert kept == st["intra_edges"]
+    want_batches = ref.cluster_batches(tr, n, ref_lab, parts)
+    assert all(torch.equal(cd[p].edge_index.cpu(), want_batches[p]) for p in range(parts))
+
+
 # ---------------------------------------------------------------------------------------------
 # K5
 # ---------------------------------------------------------------------------------------------

@@ -176,3 +176,23 @@ def test_user_ranges_for_sharded_scoring():
         assert all(lo % 128 == 0 for lo, _ in r)                     # CTA tiles are not split across ranks
         sizes = [hi - lo for lo, hi in r]
         assert max(sizes) - min(s for s in sizes) <= 256 or nu < 128 * world
+
+
+def test_partitioner_orchestration_balanced_deterministic_and_better_than_hash():
+    """data/partition_gpu.py with the torch restatement of the voting kernel plugged in (tests/partition_ref.py): every
+    node labelled, parts within the capacity, same result twice, more intra-part edges than the hash start."""
+    import math
+    from partition_ref import torch_vote
+    from lgcn_b200.data import partition_gpu as pg
+    g = synthetic.make_graph("ml100k", seed=0)
+    tr, n, parts = g.edges("train"), g.num_nodes, 16
+    lab, st = pg.partition(tr, n, parts, g.num_users, vote=torch_vote)
+    lab2, _ = pg.partition(tr, n, parts, g.num_users, vote=torch_vote)
+    assert torch.equal(lab, lab2) and lab.shape == (n,) and int(lab.min()) >= 0 and int(lab.max()) < parts
+    assert st["max_part"] <= math.ceil(n / parts * 1.03)
+    h = pg.hash_labels(n, parts, "cpu")
+    assert st["intra_edges"] > 1.5 * int((h[tr[0]] == h[tr[1]]).sum())
+    assert st["intra_edges"] == max(st["starts"].values())
+    # one-sided graphs (no bipartite split) run too
+    lab3, st3 = pg.partition(tr, n, parts, None, vote=torch_vote)
+    assert st3["max_part"] <= math.ceil(n / parts * 1.03) and int(lab3.max()) < parts
