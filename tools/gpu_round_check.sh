@@ -8,7 +8,7 @@ TAG=${1:-r2}; NOTESTS=${2:-}
 O=gpurun_out
 mkdir -p $O
 if [ "$NOTESTS" != "notests" ]; then
-  timeout 900 python -m pytest tests -m gpu -x -q --durations=15 > $O/${TAG}_pytest_gpu.log 2>&1
+  timeout 900 python -m pytest tests -m gpu -q --durations=15 > $O/${TAG}_pytest_gpu.log 2>&1
   echo "pytest rc=$? $(tail -1 $O/${TAG}_pytest_gpu.log)"
 fi
 timeout 600 python bench.py > $O/${TAG}_bench_n1.json 2> $O/${TAG}_bench_n1.err
