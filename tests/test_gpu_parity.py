@@ -253,7 +253,10 @@ def test_train_epoch_matches_reference_golden(golden, name):
     assert abs(rec - float(gd["val_recall"])) < 2e-2 * float(gd["val_recall"])
     # The two tolerances above carry the Adam sensitivity of the two training steps before (tests/conftest.py).  Where the
     # fixture holds the reference's post-training weights in full (row_stride 1), evaluate() is checked ON THOSE WEIGHTS:
-    # loss to the north-star tolerance, the sampled recall to a few hit quanta (one hit = 1 / (1000 P) of it).
+    # loss to the north-star tolerance.  The sampled recall keeps a 1e-2 band even then: its candidate pool [pos; neg] holds
+    # the same item several times (negatives are drawn with replacement and may repeat positives), so exact score ties
+    # straddle the top-k cut and torch.topk's tie order (the reference) differs from the kernel's (score desc, id asc):
+    # measured 4.4e-3 relative on identical weights.
     if s == 1:
         m2 = _model(g.num_users, g.num_items, k, _t(gd["user_w_after"]), _t(gd["item_w_after"]))
         vl2 = float(tt.eval_loss(m2, val, vn))
