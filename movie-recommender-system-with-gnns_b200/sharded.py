@@ -288,6 +288,7 @@ class CudaOps:
                 raise lib_.LgcnError(f"shard has {g.num_triplets} user->movie edges, trip_global {trip_global_dev.numel()}")
             lib_.check(self.L.lgcn_graph_remap_triplets(g.ref, trip_global_dev.data_ptr(), self._s()))
         self.g = g
+        self.graph_version = getattr(self, "graph_version", 0) + 1   # a captured step holds the OLD arrays' addresses
         self._pack_tasks()
         self.index_triplets()
 
@@ -384,12 +385,12 @@ class CudaOps:
         (_, _), (ib, ie) = self.segs
         self._lib.check(self.L.lgcn_bpr_buckets(neg.data_ptr(), self.P, ib - self.nu, ie - self.nu,
                                                 self.neg_count.data_ptr(), byref(self.bpr_ws), self._s()))
-        self._buckets_for = neg.data_ptr()
+        self._buckets_for = neg                    # the tensor itself: it stays alive (no address reuse) until bpr()
 
     def bpr(self, neg):
         (_, _), (ib, ie) = self.segs
         c = self.local_bpr
-        prebuilt = getattr(self, "_buckets_for", None) == neg.data_ptr()
+        prebuilt = getattr(self, "_buckets_for", None) is neg
         self._buckets_for = None
         fn = self.L.lgcn_bpr_owner_passes if prebuilt else self.L.lgcn_bpr_owner
         self._lib.check(fn(
@@ -507,6 +508,9 @@ class ShardedTrainer:
         whole step -- sampling, kernels, peer barriers -- is replayed as ONE CUDA graph launch per rank."""
         ni = self.plan.num_items if num_items is None else num_items
         p, dev = self.ops.num_triplets, self.user_w.device
+        if getattr(self, "_graph_for", None) != getattr(self.ops, "graph_version", 0):
+            self.drop_graph()                          # the edge list was reloaded since the capture
+            self._graph_for = getattr(self.ops, "graph_version", 0)
         self._calls = getattr(self, "_calls", 0) + 1
         if not use_graph or not self.user_w.is_cuda or getattr(self, "_graph_failed", False):
             return self.step(None, ni)
